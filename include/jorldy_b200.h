@@ -1,0 +1,129 @@
+/* jorldy_b200 — C ABI of the B200-native rollout-collect -> buffer -> learn() core.
+ *
+ * The reference (kakaoenterprise/JORLDY) is pure Python and has no FFI of its own; its plugin
+ * boundary is the Python classes Agent / Env / Buffer / Network / Optimizer.  This header is the
+ * boundary a maintainer would bind from those classes (ctypes stub in INTEGRATION.md): plain
+ * pointers and sizes, no torch types.  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says host; buffers are caller-owned
+ *     (the Python host allocates them as torch tensors) and must stay alive until the stream
+ *     has drained;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (async w.r.t. host);
+ *   - return value: 0 = ok, negative errno-style code otherwise (-22 bad argument, -5 CUDA
+ *     launch/runtime failure).  Nothing throws;
+ *   - one learner thread per handle/stream, as in the reference (run_mode.py:327).
+ */
+#ifndef JORLDY_B200_H
+#define JORLDY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+#define JB_API extern "C"
+#else
+#define JB_API
+#endif
+
+/* ---------------------------------------------------------------------------------------------
+ * Environments — jorldy/core/env/gym_env.py:61-83 (Cartpole.step / _Gym.reset :32-36),
+ * :86-95 (Pendulum, MountainCar) + run_mode.py:91 auto-reset line; gym 0.23.0 physics.
+ * kind: 0 cartpole (phys[n,4], obs[n,4]), 1 pendulum (phys[n,2], obs[n,3]),
+ *       2 mountain_car (phys[n,2], obs[n,2]).
+ * action_kind: 0 int64, 1 int32, 2 float32.
+ * stats (may be NULL): [2] floats, += {episodes finished, sum of their scores}.
+ * ------------------------------------------------------------------------------------------- */
+JB_API int jb_env_classic_reset(int kind, double* phys, float* obs, int32_t* elapsed, int64_t* episode,
+                                float* score, const uint8_t* mask, uint64_t seed, uint64_t stream_base,
+                                int n, void* stream);
+JB_API int jb_env_classic_step(int kind, double* phys, float* obs, int32_t* elapsed, int64_t* episode,
+                               float* score, const void* action, int action_kind, float* next_obs,
+                               float* reward, float* done, float* stats, int auto_reset, int max_steps,
+                               uint64_t seed, uint64_t stream_base, int n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GAE — jorldy/core/agent/ppo.py:95-110.  Arrays are [N,T] row-major f32.
+ * next_value may be NULL: then V(s'_t) = value[:,t+1] and last_value[N] closes the row.
+ * ------------------------------------------------------------------------------------------- */
+JB_API int jb_gae(const float* reward, const float* done, const float* value, const float* next_value,
+                  const float* last_value, int N, int T, float gamma, float lambda, int standardize,
+                  float* adv, float* ret, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PER sum-tree — jorldy/core/buffer/per_buffer.py:19-101.  tree is f64[2*capacity-1].
+ * ------------------------------------------------------------------------------------------- */
+JB_API int jb_per_update(double* tree, int64_t capacity, const int64_t* tree_idx, int64_t first_idx,
+                         const double* new_p, const double* fill_p, double* max_priority, int B,
+                         void* stream);
+JB_API int jb_per_sample(const double* tree, int64_t capacity, int64_t counter, int B, double beta,
+                         double uniform_sample_prob, const double* u_a, const double* u_b, uint64_t seed,
+                         uint64_t rng_ctr, const double* global_total, const int64_t* global_counter,
+                         int64_t* out_idx, double* out_w, double* out_p, double* out_stats, int normalize,
+                         void* stream);
+JB_API int jb_per_scale_weights(double* w, const double* wmax, int B, void* stream);
+JB_API int jb_per_rebuild(double* tree, int64_t capacity, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense layers — jorldy/core/network/head.py:6-18, q_network.py, policy_value.py, dueling.py
+ * (torch.nn.Linear: weight [out,in]) and network/utils.py:55-86 (NoisyNet: weight [in,out]).
+ * ------------------------------------------------------------------------------------------- */
+JB_API int jb_gemm(const float* A, int lda, int a_kc, const float* B, int ldb, int b_kc, float* C, int ldc,
+                   int M, int N, int K, const float* bias, int relu, const float* mask, int ldmask,
+                   float* rowsum_a, int accumulate, void* stream);
+JB_API int jb_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int in_f, int out_f,
+                         int relu, void* stream);
+JB_API int jb_linear_bwd_dx(const float* dy, const float* w, float* dx, int M, int in_f, int out_f,
+                            const float* relu_act, void* stream);
+JB_API int jb_linear_bwd_dw(const float* dy, const float* x, float* dw, float* db, int M, int in_f, int out_f,
+                            void* stream);
+JB_API int jb_linear_io_fwd(const float* x, const float* w, const float* b, float* y, int M, int in_f, int out_f,
+                            int relu, void* stream);
+JB_API int jb_linear_io_bwd_dx(const float* dy, const float* w, float* dx, int M, int in_f, int out_f,
+                               const float* relu_act, void* stream);
+JB_API int jb_linear_io_bwd_dw(const float* dy, const float* x, float* dw, int M, int in_f, int out_f, void* stream);
+JB_API int jb_colsum(const float* x, int M, int N, float* out, int accumulate, void* stream);
+JB_API int jb_mlp_in_fwd(const float* x, const int32_t* idx, const float* w1, const float* b1, int M, int D, int H,
+                         float* h1, float* xg, void* stream);
+JB_API int jb_heads_fwd(const float* h, int M, int H, const float* w0, const float* b0, int n0, const float* w1,
+                        const float* b1, int n1, const float* w2, const float* b2, int n2, float* out, void* stream);
+JB_API int jb_heads_bwd_dx(const float* dout, const float* h, int M, int H, const float* w0, int n0, const float* w1,
+                           int n1, const float* w2, int n2, float* dh, void* stream);
+JB_API int jb_heads_bwd_dw(const float* dout, const float* h, int M, int H, float* dw0, float* db0, int n0, float* dw1,
+                           float* db1, int n1, float* dw2, float* db2, int n2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PPO — jorldy/core/agent/ppo.py:54-69 (act), :83-93 (value / log_prob_old), :127-162 (loss).
+ * `out` is the [M,nout] pre-activation head output: discrete [logits(A)|v], continuous
+ * [mu(A)|log_std(A)|v].
+ * ------------------------------------------------------------------------------------------- */
+JB_API int jb_ppo_act_discrete(const float* out, int M, int A, int nout, const float* u, uint64_t seed,
+                               uint64_t stream_base, uint64_t ctr, long long* row_ctr, int greedy, int64_t* action,
+                               void* stream);
+JB_API int jb_ppo_act_continuous(const float* out, int M, int A, int nout, const float* normal, uint64_t seed,
+                                 uint64_t stream_base, uint64_t ctr, long long* row_ctr, int greedy, float* action,
+                                 void* stream);
+JB_API int jb_ppo_prepass_discrete(const float* out, const int32_t* action, int M, int A, int nout, float* value,
+                                   float* logp_old, void* stream);
+JB_API int jb_ppo_prepass_continuous(const float* out, const float* action, int M, int A, int nout, float* value,
+                                     float* logp_old, void* stream);
+JB_API int jb_take_minibatch(const int32_t* perm, long long* cursor, int B, int32_t* cur_idx, void* stream);
+JB_API int jb_ppo_loss(int continuous, const float* out, const int32_t* idx, const void* action, const float* adv,
+                       const float* ret, const float* value_old, const float* logp_old, int B, int A, int nout,
+                       float eps_clip, float vf_coef, float ent_coef, float* dout, float* stats, float* acc,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimisers — torch.optim.Adam / RMSprop(centered) via jorldy/core/optimizer/__init__.py:31,
+ * torch.nn.utils.clip_grad_norm_ (ppo.py:166-168, ape_x.py:119), target copy dqn.py:153-154.
+ * ------------------------------------------------------------------------------------------- */
+JB_API int jb_grad_partials_count(long long P);
+JB_API int jb_grad_sumsq(const float* g, long long P, float* partials, long long* step, void* stream);
+JB_API int jb_adam_step(float* p, const float* g, float* m, float* v, long long P, const float* lr, float beta1,
+                        float beta2, float eps, const long long* step, const float* partials, int n_partials,
+                        float max_norm, float* norm_out, void* stream);
+JB_API int jb_rmsprop_centered_step(float* p, const float* g, float* square_avg, float* grad_avg, long long P,
+                                    const float* lr, float alpha, float eps, const float* partials, int n_partials,
+                                    float max_norm, float* norm_out, void* stream);
+JB_API int jb_copy_f32(float* dst, const float* src, long long P, void* stream);
+
+#endif /* JORLDY_B200_H */

@@ -1,0 +1,22 @@
+"""Agent factory with the reference's registry keys (jorldy/core/agent/__init__.py:32-42)."""
+from collections import OrderedDict
+
+from .ppo import PPO
+
+agent_dict = OrderedDict(ppo=PPO)
+
+
+def register(name, cls):
+    agent_dict[name] = cls
+
+
+class Agent:
+    def __new__(cls, name, *args, **kwargs):
+        if type(name) != str:
+            print("### name variable must be string! ###")
+            raise Exception
+        name = name.lower()
+        if name not in agent_dict.keys():
+            print(f"### can use only follows {[opt for opt in agent_dict.keys()]}")
+            raise Exception
+        return agent_dict[name](*args, **kwargs)

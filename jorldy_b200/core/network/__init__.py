@@ -1,0 +1,26 @@
+"""Network factory with the reference's registry keys (jorldy/core/network/__init__.py:30-40:
+snake_case(ClassName))."""
+from collections import OrderedDict
+
+from .policy_value import DiscretePolicyValue, ContinuousPolicyValue
+
+network_dict = OrderedDict(
+    continuous_policy_value=ContinuousPolicyValue,
+    discrete_policy_value=DiscretePolicyValue,
+)
+
+
+def register(name, cls):
+    network_dict[name] = cls
+
+
+class Network:
+    def __new__(cls, name, *args, **kwargs):
+        if type(name) != str:
+            print("### name variable must be string! ###")
+            raise Exception
+        name = name.lower()
+        if name not in network_dict.keys():
+            print(f"### can use only follows {[opt for opt in network_dict.keys()]}")
+            raise Exception
+        return network_dict[name](*args, **kwargs)

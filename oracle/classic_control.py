@@ -1,0 +1,93 @@
+"""CPU restatement of the classic-control envs behind jorldy/core/env/gym_env.py.
+
+JORLDY wrapper semantics (pinned by reading the reference):
+  * Cartpole.step (gym_env.py:70-83): action.item(); continuous variant thresholds `action < 0`
+    (:74-75); score += gym reward; reward := -1 if done else 0.1 (:78); outputs expand to (1, ?).
+  * _Gym.reset (gym_env.py:32-36): score = 0, state expanded to (1, state_size).
+Physics = gym==0.23.0 classic_control (third-party, not vendored: PARITY UNPINNED, see package
+docstring), restated from its published equations with python-float (f64) state and an f32 copy
+returned as the observation, wrapped in TimeLimit (CartPole-v1: 500, Pendulum-v1 / MountainCar-v0:
+200) whose truncation also reports done=True.
+
+Batched over N envs with numpy; reset draws come from oracle.philox so they match the CUDA env.
+"""
+import math
+
+import numpy as np
+
+from . import philox
+
+
+def _reset_uniforms(seed, stream_base, env_ids, episode, n_draws):
+    """Same counter scheme as csrc/env_classic.cu: ctr = 2*episode (+1), 2 doubles per Philox call."""
+    out = []
+    for k in range((n_draws + 1) // 2):
+        a, b, c, d = philox.philox4x32(seed, stream_base + env_ids.astype(np.uint64), 2 * episode.astype(np.uint64) + np.uint64(k))
+        out.append(philox.u01_double(a, b))
+        out.append(philox.u01_double(c, d))
+    return out[:n_draws]
+
+
+class CartPoleBatch:
+    gravity = 9.8
+    masscart = 1.0
+    masspole = 0.1
+    total_mass = masspole + masscart
+    length = 0.5
+    polemass_length = masspole * length
+    force_mag = 10.0
+    tau = 0.02
+    theta_threshold_radians = 12 * 2 * math.pi / 360
+    x_threshold = 2.4
+    max_steps = 500
+
+    def __init__(self, n, seed=0, stream_base=0, auto_reset=True):
+        self.n, self.seed, self.stream_base, self.auto_reset = n, seed, stream_base, auto_reset
+        self.ids = np.arange(n, dtype=np.int64)
+        self.phys = np.zeros((n, 4), dtype=np.float64)
+        self.elapsed = np.zeros(n, dtype=np.int32)
+        self.episode = np.zeros(n, dtype=np.int64)
+        self.score = np.zeros(n, dtype=np.float32)
+
+    def _draw(self, mask):
+        u = _reset_uniforms(self.seed, np.uint64(self.stream_base), self.ids[mask], self.episode[mask], 4)
+        s = np.stack([-0.05 + 0.1 * x for x in u], axis=1)
+        self.phys[mask] = s
+        self.episode[mask] += 1
+        self.elapsed[mask] = 0
+        self.score[mask] = 0
+
+    def reset(self):
+        self._draw(np.ones(self.n, dtype=bool))
+        return self.phys.astype(np.float32)
+
+    def step(self, action):
+        a = np.asarray(action).reshape(self.n)
+        if a.dtype.kind == "f":
+            a = np.where(a < 0, 0, 1)          # gym_env.py:74-75
+        x, x_dot, theta, theta_dot = (self.phys[:, i].copy() for i in range(4))
+        force = np.where(a == 1, self.force_mag, -self.force_mag)
+        costheta, sintheta = np.cos(theta), np.sin(theta)
+        temp = (force + self.polemass_length * (theta_dot * theta_dot) * sintheta) / self.total_mass
+        thetaacc = (self.gravity * sintheta - costheta * temp) / (
+            self.length * (4.0 / 3.0 - self.masspole * (costheta * costheta) / self.total_mass))
+        xacc = temp - self.polemass_length * thetaacc * costheta / self.total_mass
+        x = x + self.tau * x_dot
+        x_dot = x_dot + self.tau * xacc
+        theta = theta + self.tau * theta_dot
+        theta_dot = theta_dot + self.tau * thetaacc
+        term = (x < -self.x_threshold) | (x > self.x_threshold) | (theta < -self.theta_threshold_radians) | (
+            theta > self.theta_threshold_radians)
+        self.elapsed += 1
+        done = term | (self.elapsed >= self.max_steps)
+        self.score += 1.0
+        self.phys = np.stack([x, x_dot, theta, theta_dot], axis=1)
+        next_obs = self.phys.astype(np.float32)
+        reward = np.where(done, -1.0, 0.1).astype(np.float32)     # gym_env.py:78
+        if self.auto_reset and done.any():
+            self._draw(done)
+        return next_obs, reward, done
+
+    @property
+    def obs(self):
+        return self.phys.astype(np.float32)

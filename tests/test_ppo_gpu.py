@@ -1,0 +1,140 @@
+"""CUDA-vs-oracle parity for the PPO path (run on the B200 box: pytest -m gpu).
+
+Tolerances (fp32, stated per output; the CUDA kernels accumulate in fp32 FFMA with a different
+summation order from torch-CPU):
+  value / log_prob_old / adv / ret : rtol 1e-4, atol 2e-5      (forward + scan)
+  unstandardised adv / ret given identical value inputs (test_gae_*) : BIT-EXACT
+  first-minibatch gradients        : rtol 2e-3, atol 2e-6
+  parameters after the whole learn(): atol 0.1*lr (Adam normalises the update to ~lr, so a
+                                      relative gradient error e moves a parameter by ~lr*e)
+  result dict (losses, ratios)     : rtol/atol 2e-4
+"""
+import numpy as np
+import pytest
+import torch
+
+import gen_inputs as G
+from helpers import check_against_golden, load_golden, ppo_oracle_inputs
+from oracle import ppo as oppo
+
+pytestmark = pytest.mark.gpu
+
+
+def _make_agent(case, **kw):
+    from jorldy_b200.core import Agent
+    net = "continuous_policy_value" if case["continuous"] else "discrete_policy_value"
+    agent = Agent("ppo", state_size=case["D"], action_size=case["A"], hidden_size=case["H"], network=net,
+                  optim_config={"name": "adam", "lr": case["lr"]}, gamma=case["gamma"],
+                  use_standardization=case["standardize"], run_step=1000, lr_decay=False, device="cuda",
+                  batch_size=case["batch_size"], n_step=case["T"], n_epoch=case["n_epoch"], _lambda=case["lam"],
+                  epsilon_clip=case["eps_clip"], vf_coef=case["vf_coef"], ent_coef=case["ent_coef"],
+                  clip_grad_norm=case["clip_grad_norm"], **kw)
+    return agent
+
+
+def _run_cuda(case, use_graph):
+    params, batch, hp, perms = ppo_oracle_inputs(case)
+    agent = _make_agent(case, use_cuda_graph=use_graph)
+    agent.network.load_state_dict(params)
+    agent._inject_perms = perms
+    dev = "cuda"
+    action = batch["action"].to(dev)
+    action = action if case["continuous"] else action.reshape(-1).to(torch.int32)
+    res = agent._learn_tensors(batch["state"].to(dev), action, batch["reward"].reshape(-1).to(dev),
+                               batch["done"].reshape(-1).to(dev), next_state=batch["next_state"].to(dev))
+    torch.cuda.synchronize()
+    return agent, res, (params, batch, hp, perms)
+
+
+@pytest.mark.parametrize("name", list(G.PPO_CASES.keys()))
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_ppo_learn_matches_reference_golden(name, use_graph, monkeypatch):
+    if use_graph:
+        import jorldy_b200.core.agent.ppo as ppo_mod
+        monkeypatch.setattr(ppo_mod, "GRAPH_CHUNK", 2)
+    case = G.PPO_CASES[name]
+    agent, res, _ = _run_cuda(case, use_graph)
+    gold = load_golden(name)
+    st = agent._st
+    pre = {"value": st["value"].cpu().numpy(), "adv": st["adv"].cpu().numpy(), "ret": st["ret"].cpu().numpy(),
+           "log_prob_old": st["logp_old"].cpu().numpy(), "next_value": st["next_value"].cpu().numpy()}
+    params_after = {k: v.cpu().numpy() for k, v in agent.network.state_dict().items()}
+    check_against_golden(gold, params_after, res, pre, rtol=1e-4, atol=0.1 * case["lr"], stat_tol=2e-4)
+
+
+@pytest.mark.parametrize("name", ["ppo_discrete_small", "ppo_continuous_small", "ppo_discrete_h512"])
+def test_ppo_first_minibatch_grads_match_oracle(name):
+    case = dict(G.PPO_CASES[name])
+    params, batch, hp, perms = ppo_oracle_inputs(case)
+    ref = oppo.learn(params, batch, hp, perms, lr=case["lr"], max_minibatches=1)
+    case1 = dict(case, n_epoch=1)
+    agent = _make_agent(case1, use_cuda_graph=False)
+    agent.network.load_state_dict(params)
+    # run the pre-pass + exactly one minibatch step by giving a 1-minibatch permutation
+    B = case["batch_size"]
+    dev = "cuda"
+    action = batch["action"].to(dev)
+    action = action if case["continuous"] else action.reshape(-1).to(torch.int32)
+    agent.batch_size = B
+    NT = batch["state"].shape[0]
+    # shrink the epoch to one minibatch: perm = first B indices of the oracle's permutation, rest dropped
+    agent._inject_perms = [np.concatenate([perms[0][:B], perms[0][:B]])[:NT] if NT <= 2 * B else perms[0]]
+    # do the pre-pass by hand and a single step
+    agent.n_epoch = 0
+    agent._learn_tensors(batch["state"].to(dev), action, batch["reward"].reshape(-1).to(dev),
+                         batch["done"].reshape(-1).to(dev), next_state=batch["next_state"].to(dev))
+    idx = torch.as_tensor(np.asarray(perms[0][:B]), dtype=torch.int32, device=dev)
+    agent._minibatch_step(agent._st, idx, B)
+    torch.cuda.synchronize()
+    for k, g in ref["first_grads"].items():
+        got = agent.network.g[k].cpu().numpy()
+        np.testing.assert_allclose(got, g.numpy(), rtol=2e-3, atol=2e-6, err_msg=k)
+
+
+def test_gae_bit_exact():
+    """Given identical value inputs the TD residual / scan / returns are bit-exact vs torch-CPU."""
+    from jorldy_b200._lib import C
+    rs = np.random.RandomState(3)
+    for (N, T) in [(5, 7), (33, 128), (64, 200)]:
+        reward = torch.from_numpy(rs.standard_normal((N * T, 1)).astype(np.float32))
+        done = torch.from_numpy((rs.uniform(size=(N * T, 1)) < 0.1).astype(np.float32))
+        value = torch.from_numpy(rs.standard_normal((N * T, 1)).astype(np.float32))
+        next_value = torch.from_numpy(rs.standard_normal((N * T, 1)).astype(np.float32))
+        adv_ref, ret_ref = oppo.gae(reward, done, value, next_value, T, 0.99, 0.95, False)
+        adv_s, _ = oppo.gae(reward, done, value, next_value, T, 0.99, 0.95, True)
+        d = lambda t: t.reshape(-1).cuda()
+        adv = torch.empty(N * T, device="cuda"); ret = torch.empty(N * T, device="cuda")
+        s = torch.cuda.current_stream().cuda_stream
+        C.jb_gae(d(reward).data_ptr(), d(done).data_ptr(), d(value).data_ptr(), d(next_value).data_ptr(), 0, N, T,
+                 0.99, 0.95, 0, adv.data_ptr(), ret.data_ptr(), s)
+        torch.cuda.synchronize()
+        assert np.array_equal(adv.cpu().numpy(), adv_ref.reshape(-1).numpy())
+        assert np.array_equal(ret.cpu().numpy(), ret_ref.reshape(-1).numpy())
+        r_, dn_, v_, nv_ = d(reward), d(done), d(value), d(next_value)
+        C.jb_gae(r_.data_ptr(), dn_.data_ptr(), v_.data_ptr(), nv_.data_ptr(), 0, N, T, 0.99, 0.95, 1,
+                 adv.data_ptr(), ret.data_ptr(), s)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(adv.cpu().numpy(), adv_s.reshape(-1).numpy(), rtol=2e-6, atol=2e-6)
+        assert np.array_equal(ret.cpu().numpy(), ret_ref.reshape(-1).numpy())
+
+
+def test_gae_value_shift_equals_next_value_path():
+    """next_value=NULL + last_value reproduces the explicit next_value path whenever
+    next_state[t] == state[t+1] on non-terminal steps (the resident rollout layout)."""
+    from jorldy_b200._lib import C
+    rs = np.random.RandomState(5)
+    N, T = 40, 96
+    value = rs.standard_normal((N, T)).astype(np.float32)
+    last = rs.standard_normal(N).astype(np.float32)
+    done = (rs.uniform(size=(N, T)) < 0.1).astype(np.float32)
+    reward = rs.standard_normal((N, T)).astype(np.float32)
+    nv = np.concatenate([value[:, 1:], last[:, None]], axis=1)
+    nv = np.where(done > 0, rs.standard_normal((N, T)).astype(np.float32), nv)   # garbage where done
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    r, d, v, n, l = t(reward), t(done), t(value), t(nv), t(last)
+    a1 = torch.empty(N * T, device="cuda"); r1 = torch.empty_like(a1); a2 = torch.empty_like(a1); r2 = torch.empty_like(a1)
+    s = torch.cuda.current_stream().cuda_stream
+    C.jb_gae(r.data_ptr(), d.data_ptr(), v.data_ptr(), n.data_ptr(), 0, N, T, 0.99, 0.95, 1, a1.data_ptr(), r1.data_ptr(), s)
+    C.jb_gae(r.data_ptr(), d.data_ptr(), v.data_ptr(), 0, l.data_ptr(), N, T, 0.99, 0.95, 1, a2.data_ptr(), r2.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert torch.equal(a1, a2) and torch.equal(r1, r2)
