@@ -89,6 +89,7 @@ class PPO(BaseAgent):
         self.allreduce = None
         self._inject_perms = None             # tests: list of per-epoch index arrays
         self.n_launches = 0                   # kernels launched by the last learn() (bench bookkeeping)
+        self.n_prepass_launches = 0
 
     # ------------------------------------------------------------------------------------- act --
     @property
@@ -247,6 +248,8 @@ class PPO(BaseAgent):
                 self._minibatch_step(st, st["perm"][n_full * B:], tail)
             n_steps += n_full + (1 if tail else 0)
         self.n_launches = n_steps * self.LAUNCHES_PER_MINIBATCH
+        n_chunks = (NT + 16383) // 16384
+        self.n_prepass_launches = 3 * n_chunks + 1 + 3 + 1      # forward chunks + prepass + V(s') + gae
 
         acc = torch.cat([self._acc[:6], mean_ret.view(1)]).cpu().numpy()     # ONE device->host read
         cnt = max(acc[5], 1.0)

@@ -18,7 +18,9 @@ class RolloutCollector:
                                      device=agent.device)
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
-        self.launches_per_step = None
+        # kernels of OUR library per env step: mlp_in_fwd + gemm + heads_fwd + act + env_step (the
+        # rollout-row copies are torch plumbing and not counted)
+        self.launches_per_collect = 5 * self.T
         env.reset_device()
 
     def _collect_eager(self):

@@ -1,0 +1,29 @@
+"""Multi-GPU learner plumbing: one process per GPU, torch.distributed (NCCL over NVLink 5 /
+NVSwitch) for the only real exchange step of the PPO path — the gradient all-reduce between
+backward and the clip+Adam launch.  Collection, GAE and advantage standardisation
+are per-env-row and never cross ranks.  The reference has no counterpart (single learner; ray
+actors only collect: manager/distributed_manager.py:7-65).
+
+Known, documented deviation at world_size > 1: `critic_loss = max(mean1, mean2)` (ppo.py:151-154)
+is evaluated per rank on its local minibatch shard (a 2-float all-reduce before backward would
+make it global; at B=256/rank the two means are equal in all but the clipped-value regime).
+"""
+import torch
+import torch.distributed as dist
+
+
+def attach(agent, world_size):
+    """Makes `agent` a data-parallel learner: identical initial weights on every rank (broadcast from
+    rank 0) and an averaged flat gradient before every optimiser step."""
+    if world_size <= 1:
+        return agent
+    dist.broadcast(agent.network.flat, src=0)
+    if hasattr(agent, "target_network"):
+        dist.broadcast(agent.target_network.flat, src=0)
+    agent.world_size = world_size
+
+    def allreduce(flat_grad):
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
+
+    agent.allreduce = allreduce
+    return agent

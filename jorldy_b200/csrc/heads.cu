@@ -47,9 +47,11 @@ struct HeadGradRows {
 };
 
 // out[m, o] = b[o] + sum_j h[m, j] * W[o, j] for up to 3 heads concatenated along o.
-// One warp per row: lanes stride over j (coalesced reads of h and of every W row).
-__global__ void heads_fwd_kernel(const float* __restrict__ h, int M, int H, HeadRows hr, int nout,
-                                 float* __restrict__ out) {
+// One warp per row.  The j loop is unrolled 4-deep with every load of an unrolled group issued
+// before its first use (these kernels are pure load-latency chains at minibatch sizes: the ncu
+// launch list showed one full memory latency per un-pipelined iteration).
+__global__ void __launch_bounds__(256)
+heads_fwd_kernel(const float* __restrict__ h, int M, int H, HeadRows hr, int nout, float* __restrict__ out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -57,7 +59,23 @@ __global__ void heads_fwd_kernel(const float* __restrict__ h, int M, int H, Head
 #pragma unroll
   for (int o = 0; o < MAX_NOUT; ++o) acc[o] = 0.f;
   const float* hrow = h + (size_t)warp * H;
-  for (int j = lane; j < H; j += 32) {
+  int j = lane;
+  for (; j + 96 < H; j += 128) {
+    float hv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) hv[u] = hrow[j + 32 * u];
+#pragma unroll
+    for (int o = 0; o < MAX_NOUT; ++o) {
+      if (o < nout) {
+        float wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wv[u] = hr.w[o][j + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[o] = fmaf(hv[u], wv[u], acc[o]);
+      }
+    }
+  }
+  for (; j < H; j += 32) {
     const float hv = hrow[j];
 #pragma unroll
     for (int o = 0; o < MAX_NOUT; ++o)
@@ -89,40 +107,62 @@ __global__ void heads_bwd_dx_kernel(const float* __restrict__ dout, const float*
 }
 
 // dW[o, j] = sum_m dout[m, o] * h[m, j];  db[o] = sum_m dout[m, o].
-// CTA = 32 columns (j) x 8 row-lanes; fixed-order smem reduction over the 8 row-lanes.
-__global__ void heads_bwd_dw_kernel(const float* __restrict__ dout, const float* __restrict__ h, int M, int H,
-                                    HeadGradRows gr, int nout) {
-  __shared__ float s[8][MAX_NOUT + 1][33];
+// CTA = 32 columns (j) x DW_ROWS row-lanes, each row-lane strides over the batch with a 4-deep
+// unrolled, load-first loop; fixed-order smem reduction over the row-lanes.
+constexpr int DW_ROWS = 32;
+__global__ void __launch_bounds__(32 * DW_ROWS)
+heads_bwd_dw_kernel(const float* __restrict__ dout, const float* __restrict__ h, int M, int H, HeadGradRows gr, int nout) {
+  __shared__ float s[DW_ROWS][33];
   const int j = blockIdx.x * 32 + threadIdx.x;
+  const int ry = threadIdx.y;
   float acc[MAX_NOUT];
 #pragma unroll
   for (int o = 0; o < MAX_NOUT; ++o) acc[o] = 0.f;
   float bacc = 0.f;   // lane x < nout of CTA 0 accumulates the bias gradient of output x
-  for (int m = threadIdx.y; m < M; m += 8) {
+  const bool do_b = (blockIdx.x == 0) && (threadIdx.x < nout);
+  int m = ry;
+  for (; m + 3 * DW_ROWS < M; m += 4 * DW_ROWS) {
+    float hv[4], bv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) hv[u] = (j < H) ? h[(size_t)(m + u * DW_ROWS) * H + j] : 0.f;
+    if (do_b) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) bv[u] = dout[(size_t)(m + u * DW_ROWS) * nout + threadIdx.x];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) bacc += bv[u];
+    }
+#pragma unroll
+    for (int o = 0; o < MAX_NOUT; ++o) {
+      if (o < nout) {
+        float dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dv[u] = dout[(size_t)(m + u * DW_ROWS) * nout + o];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[o] = fmaf(dv[u], hv[u], acc[o]);
+      }
+    }
+  }
+  for (; m < M; m += DW_ROWS) {
     const float hv = (j < H) ? h[(size_t)m * H + j] : 0.f;
     const float* dr = dout + (size_t)m * nout;
 #pragma unroll
     for (int o = 0; o < MAX_NOUT; ++o)
       if (o < nout) acc[o] = fmaf(dr[o], hv, acc[o]);
-    if (blockIdx.x == 0 && threadIdx.x < nout) bacc += dr[threadIdx.x];
+    if (do_b) bacc += dr[threadIdx.x];
   }
+  // one output at a time through a [DW_ROWS][33] staging tile (keeps static smem small)
+  for (int o = 0; o <= nout; ++o) {
+    float v = bacc;
 #pragma unroll
-  for (int o = 0; o < MAX_NOUT; ++o)
-    if (o < nout) s[threadIdx.y][o][threadIdx.x] = acc[o];
-  s[threadIdx.y][MAX_NOUT][threadIdx.x] = bacc;
-  __syncthreads();
-  if (threadIdx.y == 0) {
-    if (j < H) {
-      for (int o = 0; o < nout; ++o) {
-        float t = s[0][o][threadIdx.x];
-        for (int r = 1; r < 8; ++r) t += s[r][o][threadIdx.x];
-        gr.dw[o][j] = t;
-      }
-    }
-    if (blockIdx.x == 0 && threadIdx.x < nout) {
-      float t = s[0][MAX_NOUT][threadIdx.x];
-      for (int r = 1; r < 8; ++r) t += s[r][MAX_NOUT][threadIdx.x];
-      *gr.db[threadIdx.x] = t;
+    for (int q = 0; q < MAX_NOUT; ++q) if (q == o) v = acc[q];
+    __syncthreads();
+    s[ry][threadIdx.x] = v;
+    __syncthreads();
+    if (ry == 0) {
+      float t = s[0][threadIdx.x];
+      for (int r = 1; r < DW_ROWS; ++r) t += s[r][threadIdx.x];
+      if (o < nout) { if (j < H) gr.dw[o][j] = t; }
+      else if (do_b) *gr.db[threadIdx.x] = t;
     }
   }
 }
@@ -189,6 +229,6 @@ JB_API int jb_heads_bwd_dw(const float* dout, const float* h, int M, int H, floa
       gr.db[o] = db[g] + q;
     }
   for (; o < MAX_NOUT; ++o) { gr.dw[o] = nullptr; gr.db[o] = nullptr; }
-  heads_bwd_dw_kernel<<<jb_div_up(H, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(dout, h, M, H, gr, nout);
+  heads_bwd_dw_kernel<<<jb_div_up(H, 32), dim3(32, DW_ROWS), 0, (cudaStream_t)stream>>>(dout, h, M, H, gr, nout);
   return jb_check_launch();
 }

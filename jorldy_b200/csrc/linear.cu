@@ -199,6 +199,180 @@ gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, i
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// "panel" kernel for the minibatch-sized products (a few hundred 32x32 tiles): the whole K extent
+// of the tile (up to 512) is staged in shared memory with cp.async (LDGSTS, 16-byte chunks, every
+// request in flight at once, four commit groups so compute starts when the first quarter lands)
+// instead of the register-staged 32-deep loop above, whose 16 exposed L2 round trips per tile
+// dominated its run time at one CTA per SM.  Threads: 4 k-groups x (8 x 8) with a 4x4 micro-tile;
+// a k-contiguous operand is kept [row][k] (+4 pad) and read as float4 along k with the rows
+// interleaved (r = t + 8 i) so a quarter-warp's 16-byte reads hit distinct banks; a row-major-in-k
+// operand is kept [k][32] (+4 pad) and read as float4 along the tile row.  Requires 16-byte aligned
+// rows (ld % 4 == 0, K % 4 == 0); other shapes take the generic kernel.
+constexpr int PK = 512;          // panel depth
+constexpr int PCH = 128;         // k per commit group
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <bool KC>
+__device__ __forceinline__ void panel_issue(float* sm, const float* __restrict__ G, int ld, int r0, int R, int k0,
+                                            int K, int kp, int c /*chunk*/, int tid) {
+  // stage rows [r0, r0+32) x k [k0 + c*PCH, +PCH) of operand G into sm
+  const int kbase = c * PCH;
+  if (kbase >= kp) return;
+  if (KC) {
+    const int stride = kp + 4;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + r * 256;
+      const int row = e >> 5, c16 = e & 31;
+      const int k = kbase + c16 * 4;
+      if (k < kp) {
+        const int gr = r0 + row, gk = k0 + k;
+        const bool ok = (gr < R) && (gk < K);
+        cp_async16(&sm[row * stride + k], ok ? (const void*)&G[(size_t)gr * ld + gk] : (const void*)G, ok ? 16 : 0);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + r * 256;
+      const int krow = e >> 3, c16 = e & 7;
+      const int k = kbase + krow;
+      if (k < kp) {
+        const int gk = k0 + k, gr = r0 + c16 * 4;
+        const bool ok = (gk < K) && (gr < R);     // R % 4 == 0 guaranteed by the launcher when !KC
+        cp_async16(&sm[k * 36 + c16 * 4], ok ? (const void*)&G[(size_t)gk * ld + gr] : (const void*)G, ok ? 16 : 0);
+      }
+    }
+  }
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256)
+gemm_panel_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                  float* __restrict__ C, int ldc, int M, int N, int K,
+                  const float* __restrict__ bias, int relu, const float* __restrict__ mask, int ldmask,
+                  float* __restrict__ rowsum_a, int accumulate, int kp /* staged depth, multiple of 16, <= PK */) {
+  extern __shared__ __align__(16) float psm[];
+  const int a_floats = A_KC ? 32 * (kp + 4) : kp * 36;
+  float* As = psm;
+  float* Bs = psm + a_floats;
+  const int tid = threadIdx.x;
+  const int grp = tid >> 6, t = tid & 63, tx = t & 7, ty = t >> 3;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const bool do_rowsum = (rowsum_a != nullptr) && (blockIdx.x == 0);
+  const int a_stride = kp + 4, b_stride = kp + 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float rs[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int k0 = 0; k0 < K; k0 += kp) {
+    if (k0 > 0) __syncthreads();               // previous panel fully consumed
+#pragma unroll
+    for (int c = 0; c < PK / PCH; ++c) {
+      panel_issue<A_KC>(As, A, lda, m0, M, k0, K, kp, c, tid);
+      panel_issue<B_KC>(Bs, B, ldb, n0, N, k0, K, kp, c, tid);
+      cp_async_commit();
+    }
+#pragma unroll
+    for (int c = 0; c < PK / PCH; ++c) {
+      if (c == 0) cp_async_wait<3>(); else if (c == 1) cp_async_wait<2>(); else if (c == 2) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncthreads();
+      const int kend = min(kp, (c + 1) * PCH);
+      for (int k = c * PCH + grp * 4; k < kend; k += 16) {
+        float a[4][4], b[4][4];               // [row i][k q]
+        if (A_KC) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(&As[(ty + 8 * i) * a_stride + k]);
+            a[i][0] = v.x; a[i][1] = v.y; a[i][2] = v.z; a[i][3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(&As[(k + q) * 36 + ty * 4]);
+            a[0][q] = v.x; a[1][q] = v.y; a[2][q] = v.z; a[3][q] = v.w;
+          }
+        }
+        if (B_KC) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(&Bs[(tx + 8 * j) * b_stride + k]);
+            b[j][0] = v.x; b[j][1] = v.y; b[j][2] = v.z; b[j][3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(&Bs[(k + q) * 36 + tx * 4]);
+            b[0][q] = v.x; b[1][q] = v.y; b[2][q] = v.z; b[3][q] = v.w;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i][q], b[j][q], acc[i][j]);
+        if (do_rowsum) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rs[i] += (a[i][0] + a[i][1]) + (a[i][2] + a[i][3]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // fixed-order reduction over the 4 k-groups
+  float (*red)[32][33] = reinterpret_cast<float (*)[32][33]>(psm);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = A_KC ? (ty + 8 * i) : (ty * 4 + i);
+      const int cc = B_KC ? (tx + 8 * j) : (tx * 4 + j);
+      red[grp][r][cc] = acc[i][j];
+    }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int e = tid + r * 256;
+    const int m = e >> 5, n = e & 31;
+    float v = (red[0][m][n] + red[1][m][n]) + (red[2][m][n] + red[3][m][n]);
+    const int gm = m0 + m, gn = n0 + n;
+    if (gm < M && gn < N) {
+      if (bias) v += bias[gn];
+      if (relu) v = fmaxf(v, 0.f);
+      if (mask) v = (mask[(size_t)gm * ldmask + gn] > 0.f) ? v : 0.f;
+      float* dst = &C[(size_t)gm * ldc + gn];
+      *dst = accumulate ? (*dst + v) : v;
+    }
+  }
+  if (do_rowsum) {
+    __syncthreads();
+    float* rsm = psm;   // [4][32]
+    if (tx == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rsm[grp * 32 + (A_KC ? (ty + 8 * i) : (ty * 4 + i))] = rs[i];
+    }
+    __syncthreads();
+    if (tid < 32 && m0 + tid < M) {
+      const float v = (rsm[tid] + rsm[32 + tid]) + (rsm[64 + tid] + rsm[96 + tid]);
+      rowsum_a[m0 + tid] = accumulate ? (rowsum_a[m0 + tid] + v) : v;
+    }
+  }
+}
+
 template <bool A_KC, bool B_KC>
 int launch_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
                 const float* bias, int relu, const float* mask, int ldmask, float* rowsum_a, int accumulate,
@@ -211,8 +385,24 @@ int launch_gemm(const float* A, int lda, const float* B, int ldb, float* C, int 
                                                                        mask, ldmask, rowsum_a, accumulate);
   } else {
     dim3 grid(jb_div_up(N, 32), jb_div_up(M, 32));
-    gemm_kernel<32, 32, 32, 4, 4, 4, A_KC, B_KC><<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, relu,
-                                                                      mask, ldmask, rowsum_a, accumulate);
+    const bool aligned = (lda % 4 == 0) && (ldb % 4 == 0) && (K % 4 == 0) && (((uintptr_t)A & 15) == 0) &&
+                         (((uintptr_t)B & 15) == 0) && (A_KC || M % 4 == 0) && (B_KC || N % 4 == 0);
+    if (aligned && K >= 32) {
+      int kp = K >= PK ? PK : ((K + 15) / 16) * 16;
+      size_t smem = sizeof(float) * (size_t)((A_KC ? 32 * (kp + 4) : kp * 36) + (B_KC ? 32 * (kp + 4) : kp * 36));
+      const size_t red = sizeof(float) * 4 * 32 * 33;
+      if (smem < red) smem = red;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaFuncSetAttribute(gemm_panel_kernel<A_KC, B_KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set = true;
+      }
+      gemm_panel_kernel<A_KC, B_KC><<<grid, 256, smem, s>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, relu, mask, ldmask,
+                                                         rowsum_a, accumulate, kp);
+    } else {
+      gemm_kernel<32, 32, 32, 4, 4, 4, A_KC, B_KC><<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, relu,
+                                                                        mask, ldmask, rowsum_a, accumulate);
+    }
   }
   return jb_check_launch();
 }

@@ -43,15 +43,31 @@ grad_sumsq_kernel(const float* __restrict__ g, long long P, float* __restrict__ 
   }
 }
 
+// Every CTA folds the per-CTA partials: thread-strided loads (all in flight at once), f64
+// butterfly per warp, then a fixed-order fold of the warp sums — identical in every CTA and run.
+// Must be called by all threads of a 256-thread block.
 __device__ __forceinline__ float clip_coef_from_partials(const float* __restrict__ partials, int n_partials,
                                                          float max_norm, float* norm_out) {
+  __shared__ double s_w[8];
+  __shared__ float s_coef;
   double t = 0.0;
-  for (int k = 0; k < n_partials; ++k) t += (double)partials[k];
-  const float total_norm = (float)sqrt(t);
-  if (norm_out) *norm_out = total_norm;
-  if (max_norm <= 0.f) return 1.f;
-  const float c = max_norm / (total_norm + 1e-6f);
-  return c < 1.f ? c : 1.f;
+  for (int k = threadIdx.x; k < n_partials; k += 256) t += (double)partials[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_w[w];
+    const float total_norm = (float)sqrt(tot);
+    if (norm_out) *norm_out = total_norm;
+    float c = 1.f;
+    if (max_norm > 0.f) { c = max_norm / (total_norm + 1e-6f); c = c < 1.f ? c : 1.f; }
+    s_coef = c;
+  }
+  __syncthreads();
+  return s_coef;
 }
 
 struct AdamHP { float b1, b2, eps, max_norm; };
@@ -60,11 +76,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             long long P, const float* __restrict__ lr_ptr, AdamHP hp, const long long* __restrict__ step_ptr,
             const float* __restrict__ partials, int n_partials, float* __restrict__ norm_out) {
-  __shared__ float s_coef;
-  if (threadIdx.x == 0)
-    s_coef = clip_coef_from_partials(partials, n_partials, hp.max_norm, blockIdx.x == 0 ? norm_out : nullptr);
-  __syncthreads();
-  const float coef = s_coef;
+  const float coef = clip_coef_from_partials(partials, n_partials, hp.max_norm, blockIdx.x == 0 ? norm_out : nullptr);
   const double t = (double)(*step_ptr);
   const double bc1 = 1.0 - pow((double)hp.b1, t);
   const double bc2 = 1.0 - pow((double)hp.b2, t);
@@ -102,11 +114,7 @@ __global__ void __launch_bounds__(256)
 rmsprop_centered_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq,
                         float* __restrict__ ga, long long P, const float* __restrict__ lr_ptr, RmsHP hp,
                         const float* __restrict__ partials, int n_partials, float* __restrict__ norm_out) {
-  __shared__ float s_coef;
-  if (threadIdx.x == 0)
-    s_coef = clip_coef_from_partials(partials, n_partials, hp.max_norm, blockIdx.x == 0 ? norm_out : nullptr);
-  __syncthreads();
-  const float coef = s_coef;
+  const float coef = clip_coef_from_partials(partials, n_partials, hp.max_norm, blockIdx.x == 0 ? norm_out : nullptr);
   const float lr = *lr_ptr;
   const float one_m_a = 1.f - hp.alpha;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {

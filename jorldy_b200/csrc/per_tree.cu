@@ -35,7 +35,7 @@ __device__ __forceinline__ bool is_proper_ancestor(uint32_t a_plus1, uint32_t x_
 // reference: the K uniformly-drawn slots first, then the B-K prioritised ones (per_buffer.py:84).
 // u_a[B], u_b[B]: uniforms in [0,1); slot s is "uniform" iff it is among the first K = #{u_a < usp}
 // slots, uses floor(u_b[s]*counter) as ring index if uniform, u_b[s]*total as descent target otherwise.
-__global__ void per_sample_kernel(const double* __restrict__ tree, int64_t first_leaf, int64_t counter,
+__global__ void __launch_bounds__(512) per_sample_kernel(const double* __restrict__ tree, int64_t first_leaf, int64_t counter,
                                   int B, double beta, double usp, const double* __restrict__ u_a,
                                   const double* __restrict__ u_b, uint64_t seed, uint64_t rng_ctr,
                                   const double* __restrict__ global_total, const int64_t* __restrict__ global_counter,
@@ -261,7 +261,7 @@ JB_API int jb_per_sample(const double* tree, int64_t capacity, int64_t counter, 
                          void* stream) {
   if (!tree || capacity <= 0 || counter <= 0 || B <= 0 || !out_idx || !out_w || !out_p || !out_stats)
     return JB_ERR_INVALID;
-  const int threads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
+  const int threads = B >= 512 ? 512 : ((B + 31) / 32) * 32;
   per_sample_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(tree, capacity - 1, counter, B, beta, uniform_sample_prob,
                                                              u_a, u_b, seed, rng_ctr, global_total, global_counter,
                                                              out_idx, out_w, out_p, out_stats, normalize);

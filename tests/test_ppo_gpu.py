@@ -105,12 +105,12 @@ def test_gae_bit_exact():
         d = lambda t: t.reshape(-1).cuda()
         adv = torch.empty(N * T, device="cuda"); ret = torch.empty(N * T, device="cuda")
         s = torch.cuda.current_stream().cuda_stream
-        C.jb_gae(d(reward).data_ptr(), d(done).data_ptr(), d(value).data_ptr(), d(next_value).data_ptr(), 0, N, T,
+        r_, dn_, v_, nv_ = d(reward), d(done), d(value), d(next_value)
+        C.jb_gae(r_.data_ptr(), dn_.data_ptr(), v_.data_ptr(), nv_.data_ptr(), 0, N, T,
                  0.99, 0.95, 0, adv.data_ptr(), ret.data_ptr(), s)
         torch.cuda.synchronize()
         assert np.array_equal(adv.cpu().numpy(), adv_ref.reshape(-1).numpy())
         assert np.array_equal(ret.cpu().numpy(), ret_ref.reshape(-1).numpy())
-        r_, dn_, v_, nv_ = d(reward), d(done), d(value), d(next_value)
         C.jb_gae(r_.data_ptr(), dn_.data_ptr(), v_.data_ptr(), nv_.data_ptr(), 0, N, T, 0.99, 0.95, 1,
                  adv.data_ptr(), ret.data_ptr(), s)
         torch.cuda.synchronize()
