@@ -113,6 +113,38 @@ JB_API int jb_ppo_loss(int continuous, const float* out, const int32_t* idx, con
                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Value-based learners — jorldy/core/agent/dqn.py:99-138, double.py:25-41, multistep.py:41-50,
+ * per.py:50-77, ape_x.py:63-116; dueling combine network/dueling.py:21-35, rainbow.py net :66-94.
+ * ------------------------------------------------------------------------------------------- */
+JB_API int jb_q_act(const float* q, int M, int A, float eps, const float* eps_rows, const float* u, uint64_t seed,
+                    uint64_t stream_base, long long* row_ctr, int64_t* action, float* q_sel, void* stream);
+JB_API int jb_dueling_fwd(const float* adv, const float* val, int B, int A, int K, float* out, void* stream);
+JB_API int jb_dueling_bwd(const float* dout, int B, int A, int K, float* dadv, float* dval, void* stream);
+JB_API int jb_td_loss(const float* q, const float* q_next, const float* qt_next, const void* action, int action_kind,
+                      const float* reward, const float* done, const double* weights, int B, int A, float gamma,
+                      float alpha, int n_step, int double_q, int loss_kind, int order, float* dq, double* prio,
+                      float* stats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Distributional learners — jorldy/core/agent/c51.py:62-135, rainbow.py:167-235, :285-292.
+ * ------------------------------------------------------------------------------------------- */
+JB_API int jb_c51_loss(const float* logits, const float* next_online, const float* next_target, const void* action,
+                       int action_kind, const float* reward, const float* done, const double* weights, const float* z,
+                       int B, int A, int K, float gamma, float v_min, float v_max, float alpha, int n_step, int variant,
+                       float* dlogits, float* kl, double* prio, float* stats, float* scratch, void* stream);
+JB_API int jb_c51_q(const float* logits, const float* z, int M, int A, int K, float* q, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NoisyNet — jorldy/core/network/utils.py:55-86 (noisy_l), factorised noise.
+ * ------------------------------------------------------------------------------------------- */
+JB_API int jb_noisy_make(const float* mu_w, const float* sig_w, const float* mu_b, const float* sig_b, int in_f,
+                         int out_f, const float* eps_i, const float* eps_j, uint64_t seed, uint64_t stream_id,
+                         long long* draw_ctr, int is_train, float* f_i, float* f_j, float* w_eff, float* b_eff,
+                         void* stream);
+JB_API int jb_noisy_grad(const float* dw_eff, const float* db_eff, const float* f_i, const float* f_j, int in_f,
+                         int out_f, float* dmu_w, float* dsig_w, float* dmu_b, float* dsig_b, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimisers — torch.optim.Adam / RMSprop(centered) via jorldy/core/optimizer/__init__.py:31,
  * torch.nn.utils.clip_grad_norm_ (ppo.py:166-168, ape_x.py:119), target copy dqn.py:153-154.
  * ------------------------------------------------------------------------------------------- */

@@ -2,8 +2,10 @@
 from collections import OrderedDict
 
 from .ppo import PPO
+from .dqn import DQN, Double, Dueling, Multistep, PER, Noisy, C51, Rainbow, ApeX
 
-agent_dict = OrderedDict(ppo=PPO)
+agent_dict = OrderedDict(sorted(dict(ape_x=ApeX, c51=C51, double=Double, dqn=DQN, dueling=Dueling, multistep=Multistep,
+                                     noisy=Noisy, per=PER, ppo=PPO, rainbow=Rainbow).items()))
 
 
 def register(name, cls):

@@ -53,3 +53,89 @@ class RolloutCollector:
         self._graph.replay()
         self.rollout.t = self.T
         return self.rollout
+
+
+class NStepAssembler:
+    """Device-side n-step transition assembly for N batched envs.
+
+    Same windows as the reference's per-actor deques — multistep.py:90-104 / rainbow.py:294-308 (window of
+    n steps, next_state = last step's next_state) and ape_x.py:174-199 (window of n+1, next_state = the
+    (n+1)-th step's state, actor-side priority |G_n - q_0|) — including their behaviour of NOT clearing at
+    episode ends (windows straddle episodes and rely on the (1-done) mask).  One ring [N, L, ...] per field.
+    """
+
+    def __init__(self, n_step, apex=False, gamma=0.99):
+        self.n, self.apex, self.gamma = n_step, apex, gamma
+        self.L = n_step + 1 if apex else n_step
+        self.hist, self.count, self.pos = None, 0, 0
+
+    def push(self, tr):
+        """tr: dict of device tensors with leading dim N.  Returns an assembled batch dict or None."""
+        if self.hist is None:
+            self.hist = {k: torch.zeros((v.shape[0], self.L) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+                         for k, v in tr.items()}
+        for k, v in tr.items():
+            self.hist[k][:, self.pos].copy_(v)
+        newest = self.pos
+        self.pos = (self.pos + 1) % self.L
+        self.count = min(self.count + 1, self.L)
+        if self.count < self.L:
+            return None
+        oldest = self.pos                  # after the increment, pos points at the oldest entry
+        order = [(oldest + i) % self.L for i in range(self.L)]
+        h = self.hist
+        out = {"state": h["state"][:, oldest].clone(), "action": h["action"][:, oldest].clone()}
+        if self.apex:
+            out["next_state"] = h["state"][:, newest].clone()
+            steps = order[:-1]
+        else:
+            out["next_state"] = h["next_state"][:, newest].clone()
+            steps = order
+        sel = torch.as_tensor(steps, device=h["reward"].device)
+        out["reward"] = h["reward"].index_select(1, sel).unsqueeze(-1)      # [N, n, 1]
+        out["done"] = h["done"].index_select(1, sel).unsqueeze(-1)
+        if self.apex:
+            g = h["q"][:, newest].clone()
+            for i in reversed(range(self.n)):
+                s = steps[i]
+                g = h["reward"][:, s] + (1 - h["done"][:, s]) * self.gamma * g
+            out["priority"] = (g - h["q"][:, oldest]).abs().to(torch.float64).unsqueeze(-1)
+        return out
+
+
+class ReplayCollector:
+    """Off-policy resident loop: `update_period` batched env steps feeding the HBM replay, then one
+    agent.process() (the reference's sync loop, run_mode.py:180-187: one learn per round whatever the
+    number of transitions that arrived — SURVEY.md row D3)."""
+
+    def __init__(self, env, agent, update_period):
+        self.env, self.agent, self.update_period = env, agent, update_period
+        n = getattr(agent, "n_step", 1)
+        apex = type(agent).__name__ == "ApeX"
+        self.assembler = NStepAssembler(n, apex, agent.gamma) if (n > 1 or apex) else None
+        if apex:
+            agent.set_actor_epsilons(env.num_envs, total=max(agent.num_workers, env.num_envs, 2))
+        env.reset_device()
+
+    def run_round(self, step):
+        env, agent = self.env, self.agent
+        batches = []
+        for _ in range(self.update_period):
+            state = env.obs.clone()
+            action, q_sel = agent.act_device(agent._net_input(state), True)
+            next_obs, reward, done = env.step_device(action)
+            tr = {"state": state, "action": action.view(-1, 1), "reward": reward.clone(), "done": done.clone(),
+                  "next_state": next_obs.clone()}
+            if self.assembler is not None:
+                if self.assembler.apex:
+                    tr["q"] = q_sel.clone()
+                out = self.assembler.push({k: (v.view(v.shape[0]) if k in ("reward", "done") else v) for k, v in tr.items()})
+                if out is not None:
+                    batches.append(out)
+            else:
+                tr["reward"] = tr["reward"].view(-1, 1)
+                tr["done"] = tr["done"].view(-1, 1)
+                batches.append(tr)
+        step += self.update_period
+        result = agent.process(batches, step) if batches else {}
+        return step, result

@@ -2,11 +2,17 @@
 snake_case(ClassName))."""
 from collections import OrderedDict
 
-from .policy_value import DiscretePolicyValue, ContinuousPolicyValue
+from .policy_value import DiscretePolicyValue, ContinuousPolicyValue, DiscreteQ_Network
+from .dueling import Dueling
+from .noisy import Noisy, Rainbow
 
 network_dict = OrderedDict(
     continuous_policy_value=ContinuousPolicyValue,
     discrete_policy_value=DiscretePolicyValue,
+    discrete_q_network=DiscreteQ_Network,
+    dueling=Dueling,
+    noisy=Noisy,
+    rainbow=Rainbow,
 )
 
 

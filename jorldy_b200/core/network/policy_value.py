@@ -1,6 +1,8 @@
-"""Actor-critic networks (jorldy/core/network/policy_value.py:8-22 discrete, :38-57 continuous):
-head -> l (Linear+ReLU) -> narrow output heads.  forward_raw returns the PRE-activation head
-outputs; softmax / clamp / tanh-exp live in the fused PPO kernels (csrc/ppo.cu)."""
+"""Trunk + narrow-heads networks: head -> l (Linear+ReLU) -> up to three narrow output heads.
+
+Actor-critic (jorldy/core/network/policy_value.py:8-22 discrete, :38-57 continuous) and the plain
+Q network (q_network.py:8-20) share this shape.  forward_raw returns the PRE-activation head
+outputs; softmax / clamp / tanh-exp live in the fused agent kernels (csrc/ppo.cu)."""
 import torch
 
 from .base import FlatNetwork, init_gain, orthogonal_, MAX_ROWS_PER_PASS
@@ -17,6 +19,8 @@ class _PolicyValue(FlatNetwork):
         self.head = make_head(head, D_in, D_hidden)
         self.out_heads = self._out_heads(D_out)
         self.nout = sum(n for _, n, _ in self.out_heads)
+        self._wide = self.nout > 32
+        assert not self._wide or len(self.out_heads) == 1
         specs = self.head.specs() + [("l.weight", (D_hidden, self.head.D_head_out)), ("l.bias", (D_hidden,))]
         for name, n, _ in self.out_heads:
             specs += [(f"{name}.weight", (n, D_hidden)), (f"{name}.bias", (n,))]
@@ -43,7 +47,11 @@ class _PolicyValue(FlatNetwork):
         L.linear_fwd(h1, self.p["l.weight"], self.p["l.bias"], h2, relu=True)
         if out is None:
             out = self._buf(tag + "out", (M, self.nout))
-        L.heads_fwd(h2, self._heads_wb(), out)
+        if self._wide:      # a single wide head (e.g. C51's A*K logits): tiled GEMM instead of the row kernel
+            w, b = self._heads_wb()[0]
+            L.linear_fwd(h2, w, b, out, relu=False)
+        else:
+            L.heads_fwd(h2, self._heads_wb(), out)
         return out
 
     def forward_rows(self, x, out):
@@ -60,11 +68,29 @@ class _PolicyValue(FlatNetwork):
         h2 = self._buf(tag + "h2", (M, self.D_hidden))
         dh2 = self._buf(tag + "dh2", (M, self.D_hidden))
         dh1 = self._buf(tag + "dh1", (M, self.head.D_head_out))
-        L.heads_bwd_dw(dout, h2, self._heads_grads())
-        L.heads_bwd_dx(dout, h2, self._heads_wb(), dh2)                 # masked by relu(h2)
+        if self._wide:
+            (w, _), (dw, db) = self._heads_wb()[0], self._heads_grads()[0]
+            L.linear_bwd_dw(dout, h2, dw, db)
+            L.linear_bwd_dx(dout, w, dh2, relu_act=h2)
+        else:
+            L.heads_bwd_dw(dout, h2, self._heads_grads())
+            L.heads_bwd_dx(dout, h2, self._heads_wb(), dh2)             # masked by relu(h2)
         L.linear_bwd_dw(dh2, h1, self.g["l.weight"], self.g["l.bias"])
         L.linear_bwd_dx(dh2, self.p["l.weight"], dh1, relu_act=h1)      # masked by relu(h1)
         self.head.backward(self, dh1, M, tag)
+
+
+class DiscreteQ_Network(_PolicyValue):
+    """q_network.py:8-20: head -> l -> q."""
+
+    def _out_heads(self, D_out):
+        return [("q", D_out, "linear")]
+
+    def forward(self, x, *args, **kwargs):
+        return self.forward_raw(x, *args, **kwargs)
+
+    def backward(self, dq, M, tag="t."):
+        return self.backward_raw(dq, M, tag=tag)
 
 
 class DiscretePolicyValue(_PolicyValue):

@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 
-def attach(agent, world_size):
+def attach(agent, world_size, average_with="avg"):
     """Makes `agent` a data-parallel learner: identical initial weights on every rank (broadcast from
     rank 0) and an averaged flat gradient before every optimiser step."""
     if world_size <= 1:
@@ -23,7 +23,11 @@ def attach(agent, world_size):
     agent.world_size = world_size
 
     def allreduce(flat_grad):
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
+        if average_with == "avg":                       # NCCL: averaging fused into the collective
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
+        else:                                           # gloo (CPU tests) has no AVG
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+            flat_grad.div_(world_size)
 
     agent.allreduce = allreduce
     return agent

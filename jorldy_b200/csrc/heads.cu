@@ -11,7 +11,7 @@
 namespace {
 
 constexpr int MAX_DIN = 16;
-constexpr int MAX_NOUT = 16;
+constexpr int MAX_NOUT = 32;
 
 // h1[m, j] = relu(b1[j] + sum_i x[row(m), i] * W1[j, i]);  row(m) = idx ? idx[m] : m.
 // Optionally writes the gathered rows xg[m, :] (needed by the weight-gradient product).
@@ -154,7 +154,7 @@ heads_bwd_dw_kernel(const float* __restrict__ dout, const float* __restrict__ h,
   for (int o = 0; o <= nout; ++o) {
     float v = bacc;
 #pragma unroll
-    for (int q = 0; q < MAX_NOUT; ++q) if (q == o) v = acc[q];
+    for (int q = 0; q < MAX_NOUT; ++q) if (q == o && o < nout) v = acc[q];
     __syncthreads();
     s[ry][threadIdx.x] = v;
     __syncthreads();

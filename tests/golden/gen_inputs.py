@@ -71,3 +71,92 @@ SUBSAMPLE = 61   # large tensors are stored strided by this prime
 def subsample(a):
     a = np.asarray(a).reshape(-1)
     return a if a.size <= 8192 else a[::SUBSAMPLE].copy()
+
+
+# ---- value-based agents --------------------------------------------------------------------------
+def q_shapes(case):
+    from collections import OrderedDict
+    H, D, A = case["H"], case["D"], case["A"]
+    K = case.get("K", 51)
+    net = case["net"]
+    s = OrderedDict()
+    if net == "discrete_q_network":
+        out = A * K if case["agent"] == "c51" else A
+        s["head.l.weight"] = (H, D); s["head.l.bias"] = (H,)
+        s["l.weight"] = (H, H); s["l.bias"] = (H,)
+        s["q.weight"] = (out, H); s["q.bias"] = (out,)
+    elif net == "dueling":
+        s["head.l.weight"] = (H, D); s["head.l.bias"] = (H,)
+        for n in ("l1_a", "l1_v"):
+            s[f"{n}.weight"] = (H, H); s[f"{n}.bias"] = (H,)
+        s["l2_a.weight"] = (A, H); s["l2_a.bias"] = (A,)
+        s["l2_v.weight"] = (1, H); s["l2_v.bias"] = (1,)
+    elif net == "noisy":
+        for t, (i, o) in (("1", (H, H)), ("2", (H, A))):
+            s[f"mu_w{t}"] = (i, o); s[f"sig_w{t}"] = (i, o); s[f"mu_b{t}"] = (o,); s[f"sig_b{t}"] = (o,)
+        s["head.l.weight"] = (H, D); s["head.l.bias"] = (H,)
+    elif net == "rainbow":
+        for t, (i, o) in (("_a1", (H, H)), ("_v1", (H, H)), ("_a2", (H, A * K)), ("_v2", (H, K))):
+            s[f"mu_w{t}"] = (i, o); s[f"sig_w{t}"] = (i, o); s[f"mu_b{t}"] = (o,); s[f"sig_b{t}"] = (o,)
+        s["head.l.weight"] = (H, D); s["head.l.bias"] = (H,)
+        s["l.weight"] = (H, H); s["l.bias"] = (H,)
+    return s
+
+
+def q_params(case, seed_offset=0):
+    """Noisy (in,out) matrices get fan_in = in (make_params uses prod(shape[1:]) which is `out`; fine —
+    only determinism matters); sigma tensors are scaled down to the 0.5/sqrt(in) range."""
+    p = make_params(q_shapes(case), case["seed"] + seed_offset)
+    for k in p:
+        if k.startswith("sig_"):
+            p[k] = (0.3 * np.abs(p[k])).astype(np.float32)
+    return p
+
+
+def q_case_inputs(case):
+    rs = np.random.RandomState(case["seed"] + 7)
+    B, D, A, n = case["B"], case["D"], case["A"], case.get("n_step", 1)
+    state = (0.7 * rs.standard_normal((B, D))).astype(np.float32)
+    next_state = (0.7 * rs.standard_normal((B, D))).astype(np.float32)
+    action = rs.randint(0, A, size=(B, 1)).astype(np.int64)
+    if n == 1 and case["agent"] not in ("multistep", "rainbow", "ape_x"):
+        reward = rs.choice([0.1, -1.0, 1.0, 2.5], size=(B, 1)).astype(np.float64)
+        done = rs.uniform(size=(B, 1)) < 0.2
+    else:
+        reward = rs.choice([0.1, -1.0, 1.0, 2.5], size=(B, n, 1)).astype(np.float64)
+        done = rs.uniform(size=(B, n, 1)) < 0.15
+    weights = rs.uniform(0.2, 1.0, size=B)
+    weights = weights / weights.max()
+    indices = rs.randint(0, case.get("buffer_size", 64), size=B) + case.get("buffer_size", 64) - 1
+    n_layers = {"noisy": 2, "rainbow": 4}.get(case["net"], 0)
+    noise = None
+    if n_layers:
+        shapes = q_shapes(case)
+        tags = ["1", "2"] if case["net"] == "noisy" else ["_a1", "_v1", "_a2", "_v2"]
+        noise = []
+        for _pass in range(3):
+            layers = []
+            for t in tags:
+                i, o = shapes[f"mu_w{t}"]
+                layers.append((rs.standard_normal(i).astype(np.float32), rs.standard_normal(o).astype(np.float32)))
+            noise.append(layers)
+    return dict(state=state, next_state=next_state, action=action, reward=reward, done=done, weights=weights,
+                indices=indices, noise=noise)
+
+
+_QBASE = dict(D=4, A=3, H=64, B=16, lr=1e-3, gamma=0.99, buffer_size=64)
+Q_CASES = {
+    "dqn_small": dict(_QBASE, seed=21, agent="dqn", net="discrete_q_network"),
+    "double_small": dict(_QBASE, seed=22, agent="double", net="discrete_q_network"),
+    "dueling_small": dict(_QBASE, seed=23, agent="dueling", net="dueling"),
+    "multistep_small": dict(_QBASE, seed=24, agent="multistep", net="discrete_q_network", n_step=4),
+    "per_small": dict(_QBASE, seed=25, agent="per", net="discrete_q_network", alpha=0.6),
+    "noisy_small": dict(_QBASE, seed=26, agent="noisy", net="noisy"),
+    "c51_small": dict(_QBASE, seed=27, agent="c51", net="discrete_q_network", K=51, v_min=-1, v_max=10),
+    "rainbow_small": dict(_QBASE, seed=28, agent="rainbow", net="rainbow", K=51, v_min=-1, v_max=10, n_step=3, alpha=0.5),
+    "ape_x_small": dict(_QBASE, seed=29, agent="ape_x", net="dueling", n_step=3, alpha=0.6, clip=40.0,
+                        optim={"name": "rmsprop", "eps": 1.5e-7, "lr": 1e-3, "centered": True}),
+    "dqn_h512": dict(_QBASE, seed=30, agent="dqn", net="discrete_q_network", H=512, B=32, A=2),
+    "rainbow_h512": dict(_QBASE, seed=31, agent="rainbow", net="rainbow", H=512, B=32, A=2, K=51, v_min=-1, v_max=10,
+                         n_step=3, alpha=0.5, lr=6.25e-5),
+}

@@ -40,3 +40,38 @@ def check_against_golden(gold, params_after, result, pre=None, rtol=1e-5, atol=1
         elif k.startswith("pre.") and pre is not None and k[4:] in pre:
             got = G.subsample(np.asarray(pre[k[4:]], dtype=np.float32))
             np.testing.assert_allclose(got, v, rtol=rtol, atol=atol, err_msg=k)
+
+
+# ---- value-based agents --------------------------------------------------------------------------
+def q_oracle_inputs(case):
+    inp = G.q_case_inputs(case)
+    params = {k: torch.from_numpy(v) for k, v in G.q_params(case).items()}
+    tparams = {k: torch.from_numpy(v) for k, v in G.q_params(case, seed_offset=1000).items()}
+    batch = {"state": torch.from_numpy(inp["state"]), "next_state": torch.from_numpy(inp["next_state"]),
+             "action": torch.from_numpy(inp["action"].astype(np.float32)),
+             "reward": torch.from_numpy(inp["reward"].astype(np.float32)),
+             "done": torch.from_numpy(inp["done"].astype(np.float32)), "weights": inp["weights"]}
+    ag = case["agent"]
+    noise = None
+    if inp["noise"] is not None:
+        noise = [[(torch.from_numpy(a), torch.from_numpy(b)) for a, b in layers] for layers in inp["noise"]]
+    hp = {"action_size": case["A"], "gamma": case["gamma"], "n_step": case.get("n_step", 1),
+          "alpha": case.get("alpha", 0.0), "clip": case.get("clip"), "noise": noise,
+          "net": {"discrete_q_network": "dqn", "dueling": "dueling", "noisy": "noisy", "rainbow": "rainbow"}[case["net"]],
+          "double": ag in ("double", "per", "ape_x"), "loss": "wmse" if ag in ("per", "ape_x") else "huber",
+          "order": {"dqn": "dqn", "dueling": "dqn", "noisy": "dqn", "double": "double", "per": "double",
+                    "multistep": "nstep", "ape_x": "nstep"}.get(ag, "dqn")}
+    if ag in ("c51", "rainbow"):
+        hp.update(variant=ag, num_support=case["K"], v_min=case["v_min"], v_max=case["v_max"])
+    if ag == "noisy" and noise is not None:
+        hp["noise"] = [noise[0], None, noise[2]]
+    optim = case.get("optim", {"name": "adam", "lr": case["lr"]})
+    return params, tparams, batch, hp, optim, inp
+
+
+def run_q_oracle(case):
+    from oracle import dqn as odqn
+    params, tparams, batch, hp, optim, inp = q_oracle_inputs(case)
+    if case["agent"] in ("c51", "rainbow"):
+        return odqn.dist_learn(params, tparams, batch, hp, optim), inp
+    return odqn.td_learn(params, tparams, batch, hp, optim), inp
