@@ -113,6 +113,24 @@ JB_API int jb_ppo_loss(int continuous, const float* out, const int32_t* idx, con
                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Synthetic Atari-shaped env — observation contract of jorldy/core/env/atari.py:56-61,112,145-160.
+ * ------------------------------------------------------------------------------------------- */
+JB_API int jb_env_frames_reset(uint8_t* obs, int64_t* fcount, float* score, uint64_t seed, uint64_t stream_base, int n,
+                               void* stream);
+JB_API int jb_env_frames_step(uint8_t* obs, int64_t* fcount, float* score, uint8_t* next_obs, float* reward, float* done,
+                              float* stats, int auto_reset, uint64_t seed, uint64_t stream_base, int n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CNN head lowering — jorldy/core/network/head.py:21-61 (im2col / col2im around jb_gemm).
+ * ------------------------------------------------------------------------------------------- */
+JB_API int jb_im2col_u8(const uint8_t* x, int B, int C, int H, int W, int KH, int KW, int S, float* col, void* stream);
+JB_API int jb_im2col_nhwc(const float* x, int B, int C, int H, int W, int KH, int KW, int S, float* col, void* stream);
+JB_API int jb_col2im_nhwc(const float* dcol, int B, int C, int H, int W, int KH, int KW, int S, const float* relu_act,
+                          float* dx, void* stream);
+JB_API int jb_nhwc_to_nchw(const float* x, int B, int P, int C, float* y, void* stream);
+JB_API int jb_nchw_to_nhwc(const float* x, int B, int P, int C, const float* relu_act, float* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Value-based learners — jorldy/core/agent/dqn.py:99-138, double.py:25-41, multistep.py:41-50,
  * per.py:50-77, ape_x.py:63-116; dueling combine network/dueling.py:21-35, rainbow.py net :66-94.
  * ------------------------------------------------------------------------------------------- */

@@ -449,7 +449,8 @@ class Rainbow(PER, _Distributional):
         M = state.shape[0]
         if training and self.memory.size < max(self.batch_size, self.start_train_step):
             return torch.randint(0, self.action_size, (M,), device=self.device), None       # rainbow.py:143-147
-        logits = self.network.forward(state, training, tag=f"act{M}.", save=False)
+        logits = self.network._buf("act.logits", (M, self.action_size, self.num_support))
+        self.network.forward_rows(state, logits, is_train=training)
         return torch.argmax(self._expected_q(logits, M), -1), None
 
     def learn(self):

@@ -2,8 +2,11 @@
 from collections import OrderedDict
 
 from .classic import Cartpole, Pendulum, MountainCar
+from .frames import SyntheticAtari, _ACTIONS
 
-env_dict = OrderedDict(cartpole=Cartpole, mountain_car=MountainCar, pendulum=Pendulum)
+env_dict = OrderedDict(cartpole=Cartpole, mountain_car=MountainCar, pendulum=Pendulum, synthetic_atari=SyntheticAtari)
+for _game in _ACTIONS:            # atari.py registers one class per game (Breakout, Pong, ...)
+    env_dict[_game] = (lambda g: (lambda **kw: SyntheticAtari(name=g, **kw)))(_game)
 
 
 def register(name, cls):

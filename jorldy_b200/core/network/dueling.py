@@ -3,7 +3,7 @@
 import torch
 
 from ..dev import C, ptr, stream_ptr
-from .base import FlatNetwork, init_gain, orthogonal_, MAX_ROWS_PER_PASS
+from .base import FlatNetwork, init_gain, orthogonal_
 from .head import make_head
 from . import layers as L
 
@@ -46,8 +46,8 @@ class Dueling(FlatNetwork):
 
     def forward_rows(self, x, out):
         M = x.shape[0]
-        for s in range(0, M, MAX_ROWS_PER_PASS):
-            e = min(M, s + MAX_ROWS_PER_PASS)
+        for s in range(0, M, self.head.max_rows):
+            e = min(M, s + self.head.max_rows)
             self.forward(x[s:e], None, e - s, out[s:e], tag=f"inf{e - s}.", save=False)
         return out
 

@@ -9,7 +9,7 @@ counter — or takes injected normals `noise=[(eps_i, eps_j), ...]` for parity t
 import torch
 
 from ..dev import C, ptr, stream_ptr
-from .base import FlatNetwork, init_gain, orthogonal_, MAX_ROWS_PER_PASS
+from .base import FlatNetwork, init_gain, orthogonal_
 from .head import make_head
 from . import layers as L
 
@@ -94,8 +94,8 @@ class Noisy(FlatNetwork, _NoisyMixin):
 
     def forward_rows(self, x, out, is_train=True):
         M = x.shape[0]
-        for s in range(0, M, MAX_ROWS_PER_PASS):
-            e = min(M, s + MAX_ROWS_PER_PASS)
+        for s in range(0, M, self.head.max_rows):
+            e = min(M, s + self.head.max_rows)
             self.forward(x[s:e], is_train, None, e - s, out[s:e], tag=f"inf{e - s}.", save=False)
         return out
 
@@ -148,6 +148,14 @@ class Rainbow(FlatNetwork, _NoisyMixin):
         if out is None:
             out = self._buf(tag + "logits", (M, A, K))
         C.jb_dueling_fwd(ptr(a), ptr(v), M, A, K, ptr(out), stream_ptr())
+        return out
+
+    def forward_rows(self, x, out, is_train=True):
+        """Chunked inference (act() over many env rows); out [M, A, K]."""
+        M = x.shape[0]
+        for s in range(0, M, self.head.max_rows):
+            e = min(M, s + self.head.max_rows)
+            self.forward(x[s:e], is_train, None, e - s, out[s:e], tag=f"inf{e - s}.", save=False)
         return out
 
     def backward(self, dlogits, M, tag="t."):

@@ -5,7 +5,7 @@ Q network (q_network.py:8-20) share this shape.  forward_raw returns the PRE-act
 outputs; softmax / clamp / tanh-exp live in the fused agent kernels (csrc/ppo.cu)."""
 import torch
 
-from .base import FlatNetwork, init_gain, orthogonal_, MAX_ROWS_PER_PASS
+from .base import FlatNetwork, init_gain, orthogonal_
 from .head import make_head
 from . import layers as L
 
@@ -57,8 +57,8 @@ class _PolicyValue(FlatNetwork):
     def forward_rows(self, x, out):
         """Inference over many rows in L2-sized chunks (act() on thousands of envs, PPO pre-pass)."""
         M = x.shape[0]
-        for s in range(0, M, MAX_ROWS_PER_PASS):
-            e = min(M, s + MAX_ROWS_PER_PASS)
+        for s in range(0, M, self.head.max_rows):
+            e = min(M, s + self.head.max_rows)
             self.forward_raw(x[s:e], None, e - s, out[s:e], tag=f"inf{e - s}.", save=False)
         return out
 

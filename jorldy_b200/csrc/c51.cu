@@ -12,7 +12,11 @@
 //     v_min/v_max) l == u and BOTH weights are 0, so that atom's mass is dropped; the row is then
 //     renormalised by clamp(sum, 1e-8);
 //   * rows whose FIRST step is terminal use mean_i(onehot_l*onehot_u + lluu) instead;
-//   * Rainbow picks a* with the ONLINE net on s' (double), C51 with the TARGET net.
+//   * Rainbow picks a* with the ONLINE net on s' (double), C51 with the TARGET net;
+//   * Rainbow's IS weighting: `weights` is unsqueezed to [B,1] while KL is [B] (rainbow.py:233-235), so
+//     `(weights * KL).mean()` broadcasts to a [B,B] outer product and the loss is mean(w) * mean(KL):
+//     every sample's gradient is scaled by the batch-mean weight, not by its own.  Found by the
+//     golden-vector comparison; reproduced here (PER / Ape-X, whose td_error is [B,1], weight per sample).
 // The projection gathers contributions per output atom j in a fixed order over i (no atomics), so
 // results are bit-reproducible.
 #include "common.cuh"
@@ -125,7 +129,12 @@ c51_loss_kernel(const float* __restrict__ logits, const float* __restrict__ next
     const float g0 = (lane < K && pa0 >= 1e-8f) ? 1.f : 0.f, g1 = (lane + 32 < K && pa1 >= 1e-8f) ? 1.f : 0.f;
     const float lp0 = lane < K ? logf(fmaxf(pa0, 1e-8f)) : 0.f, lp1 = lane + 32 < K ? logf(fmaxf(pa1, 1e-8f)) : 0.f;
     const float kl = -jb_warp_sum(t0 * lp0 + t1 * lp1);
-    const float w = (hp.variant == 1 && weights) ? (float)weights[b] : 1.f;
+    float w = 1.f;                               // batch-mean IS weight (see header: [B,1] x [B] broadcast)
+    if (hp.variant == 1 && weights) {
+      float ws = 0.f;
+      for (int i = lane; i < B; i += 32) ws += (float)weights[i];
+      w = jb_warp_sum(ws) / (float)B;
+    }
     const float coef = w / (float)B;
     const float S = jb_warp_sum(t0 * g0 + t1 * g1);
     for (int a = 0; a < A; ++a) {

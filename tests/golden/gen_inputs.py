@@ -74,12 +74,25 @@ def subsample(a):
 
 
 # ---- value-based agents --------------------------------------------------------------------------
+def _head_shapes(s, case):
+    H, D = case["H"], case["D"]
+    if case.get("head", "mlp") == "cnn":
+        s["head.conv1.weight"] = (32, 4, 8, 8); s["head.conv1.bias"] = (32,)
+        s["head.conv2.weight"] = (64, 32, 4, 4); s["head.conv2.bias"] = (64,)
+        s["head.conv3.weight"] = (64, 64, 3, 3); s["head.conv3.bias"] = (64,)
+        return 3136
+    s["head.l.weight"] = (H, D); s["head.l.bias"] = (H,)
+    return H
+
+
 def q_shapes(case):
     from collections import OrderedDict
     H, D, A = case["H"], case["D"], case["A"]
     K = case.get("K", 51)
     net = case["net"]
     s = OrderedDict()
+    if case.get("head", "mlp") == "cnn":
+        return _q_shapes_cnn(case)
     if net == "discrete_q_network":
         out = A * K if case["agent"] == "c51" else A
         s["head.l.weight"] = (H, D); s["head.l.bias"] = (H,)
@@ -103,6 +116,28 @@ def q_shapes(case):
     return s
 
 
+def _q_shapes_cnn(case):
+    from collections import OrderedDict
+    H, A, K = case["H"], case["A"], case.get("K", 51)
+    s = OrderedDict()
+    if case["net"] == "discrete_q_network":
+        F = _head_shapes(s, case)
+        s["l.weight"] = (H, F); s["l.bias"] = (H,)
+        s["q.weight"] = (A, H); s["q.bias"] = (A,)
+    elif case["net"] == "dueling":
+        F = _head_shapes(s, case)
+        for n in ("l1_a", "l1_v"):
+            s[f"{n}.weight"] = (H, F); s[f"{n}.bias"] = (H,)
+        s["l2_a.weight"] = (A, H); s["l2_a.bias"] = (A,)
+        s["l2_v.weight"] = (1, H); s["l2_v.bias"] = (1,)
+    elif case["net"] == "rainbow":
+        for t, (i, o) in (("_a1", (H, H)), ("_v1", (H, H)), ("_a2", (H, A * K)), ("_v2", (H, K))):
+            s[f"mu_w{t}"] = (i, o); s[f"sig_w{t}"] = (i, o); s[f"mu_b{t}"] = (o,); s[f"sig_b{t}"] = (o,)
+        F = _head_shapes(s, case)
+        s["l.weight"] = (H, F); s["l.bias"] = (H,)
+    return s
+
+
 def q_params(case, seed_offset=0):
     """Noisy (in,out) matrices get fan_in = in (make_params uses prod(shape[1:]) which is `out`; fine —
     only determinism matters); sigma tensors are scaled down to the 0.5/sqrt(in) range."""
@@ -116,8 +151,12 @@ def q_params(case, seed_offset=0):
 def q_case_inputs(case):
     rs = np.random.RandomState(case["seed"] + 7)
     B, D, A, n = case["B"], case["D"], case["A"], case.get("n_step", 1)
-    state = (0.7 * rs.standard_normal((B, D))).astype(np.float32)
-    next_state = (0.7 * rs.standard_normal((B, D))).astype(np.float32)
+    if case.get("head", "mlp") == "cnn":
+        state = rs.randint(0, 256, size=(B, 4, 84, 84)).astype(np.uint8)
+        next_state = rs.randint(0, 256, size=(B, 4, 84, 84)).astype(np.uint8)
+    else:
+        state = (0.7 * rs.standard_normal((B, D))).astype(np.float32)
+        next_state = (0.7 * rs.standard_normal((B, D))).astype(np.float32)
     action = rs.randint(0, A, size=(B, 1)).astype(np.int64)
     if n == 1 and case["agent"] not in ("multistep", "rainbow", "ape_x"):
         reward = rs.choice([0.1, -1.0, 1.0, 2.5], size=(B, 1)).astype(np.float64)
@@ -156,6 +195,11 @@ Q_CASES = {
     "rainbow_small": dict(_QBASE, seed=28, agent="rainbow", net="rainbow", K=51, v_min=-1, v_max=10, n_step=3, alpha=0.5),
     "ape_x_small": dict(_QBASE, seed=29, agent="ape_x", net="dueling", n_step=3, alpha=0.6, clip=40.0,
                         optim={"name": "rmsprop", "eps": 1.5e-7, "lr": 1e-3, "centered": True}),
+    "dqn_cnn": dict(_QBASE, seed=32, agent="dqn", net="discrete_q_network", head="cnn", D=[4, 84, 84], A=4, B=8, H=64),
+    "rainbow_cnn": dict(_QBASE, seed=33, agent="rainbow", net="rainbow", head="cnn", D=[4, 84, 84], A=4, B=8, H=64, K=51,
+                        v_min=-1, v_max=10, n_step=3, alpha=0.5, lr=6.25e-5),
+    "ape_x_cnn": dict(_QBASE, seed=34, agent="ape_x", net="dueling", head="cnn", D=[4, 84, 84], A=4, B=8, H=64, n_step=3,
+                      alpha=0.6, clip=40.0, optim={"name": "rmsprop", "eps": 1.5e-7, "lr": 6.25e-5, "centered": True}),
     "dqn_h512": dict(_QBASE, seed=30, agent="dqn", net="discrete_q_network", H=512, B=32, A=2),
     "rainbow_h512": dict(_QBASE, seed=31, agent="rainbow", net="rainbow", H=512, B=32, A=2, K=51, v_min=-1, v_max=10,
                          n_step=3, alpha=0.5, lr=6.25e-5),

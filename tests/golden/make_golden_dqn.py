@@ -20,6 +20,8 @@ def gen_q(agent_mod, name, case):
               gamma=case["gamma"], buffer_size=case["buffer_size"], batch_size=case["B"], device="cpu", run_step=1000,
               lr_decay=False)
     ag = case["agent"]
+    if case.get("head"):
+        kw["head"] = case["head"]
     if ag in ("multistep", "rainbow", "ape_x"):
         kw["n_step"] = case["n_step"]
     if ag in ("per", "rainbow", "ape_x"):

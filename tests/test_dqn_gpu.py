@@ -20,6 +20,8 @@ def _make(case):
     kw = dict(state_size=case["D"], action_size=case["A"], hidden_size=case["H"], optim_config=dict(optim),
               gamma=case["gamma"], buffer_size=case["buffer_size"], batch_size=case["B"], device="cuda", run_step=1000,
               lr_decay=False)
+    if case.get("head"):
+        kw["head"] = case["head"]
     if ag in ("multistep", "rainbow", "ape_x"):
         kw["n_step"] = case["n_step"]
     if ag in ("per", "rainbow", "ape_x"):
