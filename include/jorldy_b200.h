@@ -130,6 +130,12 @@ JB_API int jb_col2im_nhwc(const float* dcol, int B, int C, int H, int W, int KH,
 JB_API int jb_nhwc_to_nchw(const float* x, int B, int P, int C, float* y, void* stream);
 JB_API int jb_nchw_to_nhwc(const float* x, int B, int P, int C, const float* relu_act, float* y, void* stream);
 
+/* Persistent minibatch-loop kernel (csrc/ppo_fused.cu); `host_args` points to a jb_ppo_fused_args
+ * (include/jorldy_b200_fused.h) in HOST memory. */
+JB_API int jb_ppo_fused_args_size(void);
+JB_API int jb_ppo_fused_max_ctas(void);
+JB_API int jb_ppo_fused_run(const void* host_args, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Value-based learners — jorldy/core/agent/dqn.py:99-138, double.py:25-41, multistep.py:41-50,
  * per.py:50-77, ape_x.py:63-116; dueling combine network/dueling.py:21-35, rainbow.py net :66-94.

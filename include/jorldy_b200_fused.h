@@ -1,0 +1,38 @@
+/* Argument block of the persistent PPO minibatch-loop kernel (jorldy_b200/csrc/ppo_fused.cu).
+ * Replaces the body of the epoch loop of jorldy/core/agent/ppo.py:118-175 for the MLP actor-critic
+ * networks (policy_value.py).  All pointers are device pointers; the struct itself is read on the host. */
+#ifndef JORLDY_B200_FUSED_H
+#define JORLDY_B200_FUSED_H
+#include <stdint.h>
+
+typedef struct jb_ppo_fused_args {
+  /* network: views into the flat parameter / gradient buffers */
+  float *W1, *b1, *W2, *b2;
+  float *Wh[3], *bh[3];
+  float *gW1, *gb1, *gW2, *gb2;
+  float *gWh[3], *gbh[3];
+  float *flat, *grad, *am, *av;      /* params, grads, Adam exp_avg / exp_avg_sq (flat, 16-B aligned) */
+  long long P4;                      /* number of float4 in the flat buffers */
+  /* rollout (read-only) */
+  const float *state;                /* [NT, D] */
+  const void *action;                /* int32 [NT] (discrete) or f32 [NT, A] (continuous) */
+  const float *adv, *ret, *vold, *logp_old;
+  const int32_t *perm;               /* [>= (cursor + n_steps) * B] shuffled row ids */
+  /* workspaces */
+  float *h1, *h2;                    /* [B, H] */
+  float *xg;                         /* [B, D] */
+  float *dh1;                        /* [B, H] */
+  float *rowbuf;                     /* [B, 24] */
+  float *partials;                   /* [256] per-CTA squared-norm partials */
+  float *acc;                        /* [8] learn()-level statistic accumulators */
+  int32_t *cur_idx;                  /* [B] */
+  unsigned int *barrier;             /* [1] grid-barrier counter (zeroed by the launcher) */
+  long long *step;                   /* Adam step counter (device) */
+  long long *cursor;                 /* minibatch cursor (device) */
+  const float *lr;                   /* learning rate (device scalar) */
+  int nh[3];                         /* outputs per head */
+  int B, D, H, A, nout, continuous, n_steps;
+  float eps_clip, vf_coef, ent_coef, beta1, beta2, adam_eps, max_norm;
+} jb_ppo_fused_args;
+
+#endif

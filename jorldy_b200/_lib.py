@@ -30,6 +30,8 @@ def parse_header(path=HEADER):
         name, args = m.group(1), m.group(2)
         types = []
         for a in [x.strip() for x in args.replace("\n", " ").split(",") if x.strip()]:
+            if a == "void":
+                continue
             if "*" in a:
                 types.append(ctypes.c_void_p)
                 continue
@@ -78,7 +80,7 @@ class _Caller:
     def __getattr__(self, name):
         lib = load()
         fn = getattr(lib, name)
-        raw_ok = name == "jb_grad_partials_count"
+        raw_ok = name in ("jb_grad_partials_count", "jb_ppo_fused_args_size", "jb_ppo_fused_max_ctas")
 
         def call(*args):
             rc = fn(*args)

@@ -49,6 +49,7 @@ class PPO(BaseAgent):
         num_workers=1,
         seed=0,
         use_cuda_graph=True,
+        use_fused=True,
         **kwargs,
     ):
         self.device = require_cuda(device)
@@ -82,6 +83,8 @@ class PPO(BaseAgent):
         self.rng_stream_base = 0
         self._row_ctr = {}                    # per-row Philox draw counters (device), keyed by batch rows
         self.use_cuda_graph = use_cuda_graph
+        self.use_fused = use_fused            # persistent minibatch-loop kernel (csrc/ppo_fused.cu) when eligible
+        self._fused = {}
         self._graphs = {}
         self._acc = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._cursor = torch.zeros(1, dtype=torch.int64, device=self.device)
@@ -227,7 +230,11 @@ class PPO(BaseAgent):
         self._acc[4] = float("inf")
         n_full = NT // B
         tail = NT - n_full * B
-        use_graph = self.use_cuda_graph and n_full >= GRAPH_CHUNK
+        from . import ppo_fused
+        use_fused = self.use_fused and n_full > 0 and ppo_fused.supported(self, B)
+        if use_fused and B not in self._fused:
+            self._fused[B] = ppo_fused.FusedRunner(self, B)
+        use_graph = (not use_fused) and self.use_cuda_graph and n_full >= GRAPH_CHUNK
         n_steps = 0
         for epoch in range(self.n_epoch):
             if self._inject_perms is not None:
@@ -237,6 +244,9 @@ class PPO(BaseAgent):
             st["perm"].copy_(perm)
             self._cursor.zero_()
             done_steps = 0
+            if use_fused:
+                self._fused[B].run(st, n_full)
+                done_steps = n_full
             if use_graph:
                 g = self._graph_for(st, B)
                 for _ in range(n_full // GRAPH_CHUNK):
@@ -247,7 +257,8 @@ class PPO(BaseAgent):
             if tail:
                 self._minibatch_step(st, st["perm"][n_full * B:], tail)
             n_steps += n_full + (1 if tail else 0)
-        self.n_launches = n_steps * self.LAUNCHES_PER_MINIBATCH
+        self.n_launches = (self.n_epoch * (1 + (self.LAUNCHES_PER_MINIBATCH if tail else 0)) if use_fused
+                           else n_steps * self.LAUNCHES_PER_MINIBATCH)
         n_chunks = (NT + 16383) // 16384
         self.n_prepass_launches = 3 * n_chunks + 1 + 3 + 1      # forward chunks + prepass + V(s') + gae
 

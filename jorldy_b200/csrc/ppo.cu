@@ -22,20 +22,13 @@
 // produces its rows' gradients.  All reductions are fixed-order => bit-reproducible run to run.
 #include "common.cuh"
 #include "philox.cuh"
+#include "ppo_rowmath.cuh"
 
 namespace {
 
-constexpr int MAX_A = 8;
-constexpr float F32_EPS = 1.1920928955078125e-07f;   // torch.finfo(float32).eps
-
-__device__ __forceinline__ void log_softmax_row(const float* lg, int A, float* lsm) {
-  float mx = lg[0];
-  for (int a = 1; a < A; ++a) mx = fmaxf(mx, lg[a]);
-  float s = 0.f;
-  for (int a = 0; a < A; ++a) s += expf(lg[a] - mx);
-  const float ls = logf(s);
-  for (int a = 0; a < A; ++a) lsm[a] = (lg[a] - mx) - ls;
-}
+using jbppo::MAX_A;
+using jbppo::log_softmax_row;
+using jbppo::atanh_clamped;
 
 // ---- act ------------------------------------------------------------------------------------
 __global__ void ppo_act_discrete_kernel(const float* __restrict__ out, int M, int A, int nout,
@@ -110,11 +103,6 @@ __global__ void ppo_prepass_discrete_kernel(const float* __restrict__ out, const
   value[m] = out[(size_t)m * nout + A];
 }
 
-__device__ __forceinline__ float atanh_clamped(float a) {
-  const float hi = (float)(1.0 - 1e-7), lo = (float)(-1.0 + 1e-7);
-  return atanhf(fminf(fmaxf(a, lo), hi));
-}
-
 __global__ void ppo_prepass_continuous_kernel(const float* __restrict__ out, const float* __restrict__ action,
                                               int M, int A, int nout, float* __restrict__ value,
                                               float* __restrict__ logp_old /*[M,A]*/) {
@@ -132,9 +120,7 @@ __global__ void ppo_prepass_continuous_kernel(const float* __restrict__ out, con
 }
 
 // ---- loss -------------------------------------------------------------------------------------
-struct PpoHP { float eps_clip, vf_coef, ent_coef; };
-
-// fixed-order block reduction of up to 6 floats; result broadcast to all threads
+// fixed-order block reduction; result broadcast to all threads
 template <int NV>
 __device__ __forceinline__ void block_sum(float* v, float* smem /*[NV][32]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -155,32 +141,15 @@ __device__ __forceinline__ void block_sum(float* v, float* smem /*[NV][32]*/) {
   __syncthreads();
 }
 
-// Per-row forward terms shared by the stats pass and the gradient pass.
-struct RowTerms {
-  float ratio, surr_min, ent, p_new;   // p_new = exp(log_prob) (discrete) for the min_prob stat
-  float g_ratio;                       // d min(surr1,surr2) / d ratio
-};
-
-__device__ __forceinline__ void surrogate(float ratio, float adv, float eps, float& smin, float& g) {
-  const float s1 = ratio * adv;
-  const float rc = fminf(fmaxf(ratio, 1.f - eps), 1.f + eps);
-  const float s2 = rc * adv;
-  const float inr = (ratio >= 1.f - eps && ratio <= 1.f + eps) ? 1.f : 0.f;
-  smin = fminf(s1, s2);
-  if (s1 < s2) g = adv;
-  else if (s1 > s2) g = adv * inr;
-  else g = 0.5f * adv + 0.5f * adv * inr;        // torch.minimum splits ties
-}
-
 template <bool CONT>
 __global__ void __launch_bounds__(256)
 ppo_loss_kernel(const float* __restrict__ out, const int32_t* __restrict__ idx, const void* __restrict__ action_all,
                 const float* __restrict__ adv_all, const float* __restrict__ ret_all,
                 const float* __restrict__ vold_all, const float* __restrict__ logp_old_all, int B, int A, int nout,
-                PpoHP hp, float* __restrict__ dout, float* __restrict__ stats /*[8]*/) {
-  __shared__ float sred[6 * 32];
+                jbppo::HP hp, float* __restrict__ dout, float* __restrict__ stats /*[8 + 4*n_cta]*/) {
+  __shared__ float sred[2 * 32];
   const float invB = 1.0f / (float)B;
-  // ---- pass 1 (every CTA, whole minibatch, fixed order): critic means --------------------------
+  // ---- pass 1 (every CTA, whole minibatch, fixed order): the two critic means -----------------
   float c[2] = {0.f, 0.f};
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const int r = idx ? idx[b] : b;
@@ -192,111 +161,30 @@ ppo_loss_kernel(const float* __restrict__ out, const int32_t* __restrict__ idx, 
   }
   block_sum<2>(c, sred);
   const float c1 = c[0] * invB, c2 = c[1] * invB;
-  const float w1 = (c1 > c2) ? 1.f : ((c1 == c2) ? 0.5f : 0.f);    // torch.maximum splits ties
-  const float w2 = 1.f - w1;
+  float w1, w2;
+  jbppo::critic_weights(c1, c2, w1, w2);
 
   // ---- pass 2: this CTA's rows -----------------------------------------------------------------
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  float st[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // surr_min sum, entropy sum, (unused), (unused)
+  float st[2] = {0.f, 0.f};
   float max_ratio = -INFINITY, min_prob = INFINITY;
   if (b < B) {
     const int r = idx ? idx[b] : b;
-    const float adv = adv_all[r], ret = ret_all[r], vold = vold_all[r];
+    jbppo::RowOut ro;
     const float* o = out + (size_t)b * nout;
+    if (CONT) jbppo::row<true>(o, A, 0, (const float*)action_all + (size_t)r * A, adv_all[r], ret_all[r], vold_all[r],
+                               logp_old_all + (size_t)r * A, hp, invB, ro);
+    else jbppo::row<false>(o, A, ((const int32_t*)action_all)[r], nullptr, adv_all[r], ret_all[r], vold_all[r],
+                           logp_old_all + r, hp, invB, ro);
     float* g = dout + (size_t)b * nout;
-    // value head gradient
-    const float v = o[CONT ? 2 * A : A];
-    const float dv_raw = v - vold;
-    const float vclip = vold + fminf(fmaxf(dv_raw, -hp.eps_clip), hp.eps_clip);
-    const float in_clip = (dv_raw >= -hp.eps_clip && dv_raw <= hp.eps_clip) ? 1.f : 0.f;
-    g[CONT ? 2 * A : A] = hp.vf_coef * invB * 2.f * (w1 * (v - ret) + w2 * (vclip - ret) * in_clip);
-
-    if (!CONT) {
-      const int a_t = ((const int32_t*)action_all)[r];
-      float lg[MAX_A], lsm[MAX_A], pi[MAX_A], p[MAX_A], lc[MAX_A], inr[MAX_A];
-      for (int a = 0; a < A; ++a) lg[a] = o[a];
-      log_softmax_row(lg, A, lsm);
-      float S = 0.f;
-      for (int a = 0; a < A; ++a) { pi[a] = expf(lsm[a]); S += pi[a]; }
-      float ent = 0.f;
-      for (int a = 0; a < A; ++a) {
-        p[a] = pi[a] / S;
-        const float pc = fminf(fmaxf(p[a], F32_EPS), 1.f - F32_EPS);
-        inr[a] = (p[a] >= F32_EPS && p[a] <= 1.f - F32_EPS) ? 1.f : 0.f;
-        lc[a] = logf(pc);
-        ent -= lc[a] * p[a];
-      }
-      const float logp = lc[a_t];
-      const float ratio = expf(logp - logp_old_all[r]);
-      float smin, gr;
-      surrogate(ratio, adv, hp.eps_clip, smin, gr);
-      st[0] = smin; st[1] = ent;
-      max_ratio = ratio; min_prob = expf(logp);
-      // backward
-      const float dlogp = -gr * ratio * invB;            // d(actor_loss)/d log_prob
-      const float dent = -hp.ent_coef * invB;            // d(ent_coef * entropy_loss)/d entropy_b
-      float dp[MAX_A], dot = 0.f;
-      for (int a = 0; a < A; ++a) {
-        float t = dent * (-(lc[a] + inr[a]));
-        if (a == a_t) t += dlogp * inr[a] / p[a];
-        dp[a] = t;
-        dot += t * pi[a];
-      }
-      float dlsm[MAX_A], sum_dlsm = 0.f;
-      for (int a = 0; a < A; ++a) {
-        const float dpi = dp[a] / S - dot / (S * S);
-        dlsm[a] = dpi * pi[a];
-        sum_dlsm += dlsm[a];
-      }
-      for (int a = 0; a < A; ++a) g[a] = dlsm[a] - expf(lsm[a]) * sum_dlsm;
-    } else {
-      const float* act = (const float*)action_all + (size_t)r * A;
-      const float log_sqrt_2pi = 0.9189385332046727f;
-      float dsum = 0.f, ent = 0.f;
-      float mu[MAX_A], sd[MAX_A], ls[MAX_A], z[MAX_A];
-      for (int a = 0; a < A; ++a) {
-        mu[a] = fminf(fmaxf(o[a], -5.f), 5.f);
-        ls[a] = tanhf(o[A + a]);
-        sd[a] = expf(ls[a]);
-        z[a] = atanh_clamped(act[a]);
-        const float d = z[a] - mu[a];
-        const float logp = -(d * d) / (2.f * (sd[a] * sd[a])) - logf(sd[a]) - log_sqrt_2pi;
-        dsum += logp - logp_old_all[(size_t)r * A + a];
-        ent += 0.5f + 0.5f * 1.8378770664093453f + logf(sd[a]);
-      }
-      const float ratio = expf(dsum);
-      float smin, gr;
-      surrogate(ratio, adv, hp.eps_clip, smin, gr);
-      st[0] = smin; st[1] = ent;
-      max_ratio = ratio;
-      float pmin = INFINITY;
-      for (int a = 0; a < A; ++a) {
-        const float d = z[a] - mu[a];
-        pmin = fminf(pmin, expf(-(d * d) / (2.f * (sd[a] * sd[a])) - logf(sd[a]) - log_sqrt_2pi));
-      }
-      min_prob = pmin;
-      const float dlogp = -gr * ratio * invB;
-      const float dent = -hp.ent_coef * invB / (float)A;   // entropy_loss = -mean over B*A elements
-      for (int a = 0; a < A; ++a) {
-        const float d = z[a] - mu[a];
-        const float var = sd[a] * sd[a];
-        const float dmu = dlogp * d / var;
-        const float dsd = dlogp * (d * d / (var * sd[a]) - 1.f / sd[a]) + dent / sd[a];
-        const float in_mu = (o[a] >= -5.f && o[a] <= 5.f) ? 1.f : 0.f;
-        g[a] = dmu * in_mu;
-        g[A + a] = dsd * sd[a] * (1.f - ls[a] * ls[a]);
-      }
-    }
+    const int npol = CONT ? 2 * A : A;
+    for (int a = 0; a < npol; ++a) g[a] = ro.dpol[a];
+    g[npol] = w1 * ro.dv1 + w2 * ro.dv2;
+    st[0] = ro.surr_min; st[1] = ro.ent;
+    max_ratio = ro.ratio; min_prob = ro.pmin;
   }
-  // ---- stats (CTA 0 covers rows [0, blockDim); other CTAs add via fixed slots) -----------------
-  // stats layout: [0] actor_loss [1] critic_loss [2] entropy_loss [3] max_ratio [4] min_prob
-  // Each CTA writes its partial sums to stats_partial slots; to stay single-launch and
-  // deterministic we let every CTA recompute nothing more: CTA k writes partial[k]; the host-side
-  // reader (jb_ppo_stats_finalize) folds them.  For B <= 256 (one CTA) the values are final.
-  float ssum[2] = {st[0], st[1]};
-  block_sum<2>(ssum, sred);
-  float mr = max_ratio, mp = min_prob;
-  mr = jb_warp_max(mr); mp = jb_warp_min(mp);
+  block_sum<2>(st, sred);
+  float mr = jb_warp_max(max_ratio), mp = jb_warp_min(min_prob);
   __shared__ float smax[32], smin_[32];
   if ((threadIdx.x & 31) == 0) { smax[threadIdx.x >> 5] = mr; smin_[threadIdx.x >> 5] = mp; }
   __syncthreads();
@@ -304,8 +192,8 @@ ppo_loss_kernel(const float* __restrict__ out, const int32_t* __restrict__ idx, 
     const int nw = (blockDim.x + 31) >> 5;
     for (int w = 1; w < nw; ++w) { mr = fmaxf(mr, smax[w]); mp = fminf(mp, smin_[w]); }
     float* sp = stats + 8 + 4 * blockIdx.x;     // per-CTA partials after the 8 final slots
-    sp[0] = ssum[0]; sp[1] = ssum[1]; sp[2] = mr; sp[3] = mp;
-    if (blockIdx.x == 0) { stats[1] = fmaxf(c1, c2); }
+    sp[0] = st[0]; sp[1] = st[1]; sp[2] = mr; sp[3] = mp;
+    if (blockIdx.x == 0) stats[1] = fmaxf(c1, c2);
   }
 }
 
@@ -393,7 +281,7 @@ JB_API int jb_ppo_loss(int continuous, const float* out, const int32_t* idx, con
                        void* stream) {
   if (!out || !action || !adv || !ret || !value_old || !logp_old || !dout || !stats) return JB_ERR_INVALID;
   if (B <= 0 || A <= 0 || A > MAX_A || nout != (continuous ? 2 * A + 1 : A + 1)) return JB_ERR_INVALID;
-  PpoHP hp{eps_clip, vf_coef, ent_coef};
+  jbppo::HP hp{eps_clip, vf_coef, ent_coef};
   const int n_cta = jb_div_up(B, 256);
   cudaStream_t s = (cudaStream_t)stream;
   if (continuous) ppo_loss_kernel<true><<<n_cta, 256, 0, s>>>(out, idx, action, adv, ret, value_old, logp_old, B, A, nout, hp, dout, stats);

@@ -32,9 +32,9 @@ def _make_agent(case, **kw):
     return agent
 
 
-def _run_cuda(case, use_graph):
+def _run_cuda(case, use_graph, use_fused=False):
     params, batch, hp, perms = ppo_oracle_inputs(case)
-    agent = _make_agent(case, use_cuda_graph=use_graph)
+    agent = _make_agent(case, use_cuda_graph=use_graph, use_fused=use_fused)
     agent.network.load_state_dict(params)
     agent._inject_perms = perms
     dev = "cuda"
@@ -60,6 +60,32 @@ def test_ppo_learn_matches_reference_golden(name, use_graph, monkeypatch):
            "log_prob_old": st["logp_old"].cpu().numpy(), "next_value": st["next_value"].cpu().numpy()}
     params_after = {k: v.cpu().numpy() for k, v in agent.network.state_dict().items()}
     check_against_golden(gold, params_after, res, pre, rtol=1e-4, atol=0.1 * case["lr"], stat_tol=2e-4)
+
+
+@pytest.mark.parametrize("name", list(G.PPO_CASES.keys()))
+def test_ppo_fused_kernel_matches_reference_golden(name):
+    """Persistent cooperative minibatch-loop kernel (csrc/ppo_fused.cu) against the same goldens."""
+    case = G.PPO_CASES[name]
+    if case["batch_size"] % 32:
+        pytest.skip("fused kernel needs B % 32 == 0 (host falls back to the multi-launch path)")
+    agent, res, _ = _run_cuda(case, False, use_fused=True)
+    assert agent._fused, "fused path was not taken"
+    gold = load_golden(name)
+    params_after = {k: v.cpu().numpy() for k, v in agent.network.state_dict().items()}
+    check_against_golden(gold, params_after, res, None, rtol=1e-4, atol=0.1 * case["lr"], stat_tol=2e-4)
+
+
+def test_ppo_fused_equals_multilaunch_path():
+    """Same inputs through the fused kernel and the 13-launch path: parameters agree to fp32 round-off
+    (the two paths share the row math and the Adam formula; only summation orders differ)."""
+    case = G.PPO_CASES["ppo_discrete_h512"]
+    a1, r1, _ = _run_cuda(case, False, use_fused=True)
+    a2, r2, _ = _run_cuda(case, False, use_fused=False)
+    for k in a1.network.p:
+        np.testing.assert_allclose(a1.network.p[k].cpu().numpy(), a2.network.p[k].cpu().numpy(), rtol=1e-4,
+                                   atol=0.02 * case["lr"], err_msg=k)
+    for k in r1:
+        np.testing.assert_allclose(r1[k], r2[k], rtol=1e-4, atol=1e-5, err_msg=k)
 
 
 @pytest.mark.parametrize("name", ["ppo_discrete_small", "ppo_continuous_small", "ppo_discrete_h512"])
