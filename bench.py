@@ -219,8 +219,14 @@ def main():
         agent.learning_rate_decay(step_no[0])
         return res
 
+    def log(msg):
+        if rank == 0:
+            print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+    log(f"world={world}: warm-up ({args.warmup} steps; first step captures the CUDA graphs)")
     for _ in range(args.warmup):
         res = one_step()
+    log("timing")
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -251,6 +257,9 @@ def main():
     roof = None
     cpu_base = None
     e2e = None
+    if not args.no_e2e:
+        log("e2e (plugin API, host numpy buffers) on every rank")
+        e2e = run_e2e(np, torch, Agent, Env, dev, rank, world)
     if rank == 0:
         peaks = {}
         try:
@@ -291,9 +300,6 @@ def main():
                             "fraction of the ~72 TFLOP/s fp32 FFMA peak = achieved/72"}
         else:
             roof = None
-        # ---- e2e through the plugin API with host buffers -----------------------------------------
-        if not args.no_e2e:
-            e2e = run_e2e(np, torch, Agent, Env, dev)
         # ---- cpu baseline (bounded sample) --------------------------------------------------------
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
@@ -314,11 +320,17 @@ def main():
         dist.destroy_process_group()
 
 
-def run_e2e(np, torch, Agent, Env, dev, steps=2):
-    """Same PPO iteration through agent.act(np) / env.step(np) / agent.process(list[dict], step)."""
-    env = Env("cartpole", num_envs=N_ENVS, seed=1, device=dev)
+def run_e2e(np, torch, Agent, Env, dev, rank=0, world=1, steps=2):
+    """Same PPO iteration through agent.act(np) / env.step(np) / agent.process(list[dict], step), on every rank
+    (env shard id = rank, gradient all-reduce when world > 1); wall time = max over ranks."""
+    import torch.distributed as dist
+    env = Env("cartpole", num_envs=N_ENVS, seed=1, id=rank, device=dev)
     agent = Agent("ppo", state_size=4, action_size=2, hidden_size=HIDDEN, batch_size=BATCH, n_step=N_STEP,
                   n_epoch=N_EPOCH, optim_config={"name": "adam", "lr": 2.5e-4}, device=dev, run_step=10 ** 9)
+    agent.rng_stream_base = rank << 32
+    if world > 1:
+        from jorldy_b200.core import parallel
+        parallel.attach(agent, world)
     state = env.reset()
     h2d = d2h = 0
     step = 0
@@ -340,15 +352,22 @@ def run_e2e(np, torch, Agent, Env, dev, steps=2):
 
     iteration()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     h2d = d2h = 0
     t0 = time.perf_counter()
     for _ in range(steps):
         res = iteration()
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([sec], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
     roll_bytes = N_ENVS * N_STEP * (4 * 4 * 2 + 4 + 4 + 4)      # rollout H2D at learn()
-    return {"value": N_ENVS * N_STEP * steps / sec, "unit": UNIT, "h2d_bytes_per_step": h2d // steps + roll_bytes,
-            "d2h_bytes_per_step": d2h // steps + 28, "ms_per_step": 1e3 * sec / steps, "api": "Agent.act / Env.step / Agent.process (numpy)"}
+    return {"value": world * N_ENVS * N_STEP * steps / sec, "unit": UNIT,
+            "h2d_bytes_per_step": world * (h2d // steps + roll_bytes), "d2h_bytes_per_step": world * (d2h // steps + 28),
+            "ms_per_step": 1e3 * sec / steps, "api": "Agent.act / Env.step / Agent.process (numpy, pageable host memory)"}
 
 
 if __name__ == "__main__":

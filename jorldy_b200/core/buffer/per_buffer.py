@@ -84,16 +84,35 @@ class PERBuffer(ReplayBuffer):
     # ---- sampling -------------------------------------------------------------------------------
     def sample_device(self, beta, batch_size, u_a=None, u_b=None):
         """Returns (transitions dict of device tensors, weights f64 [B], tree indices int64 [B],
-        stats f64 [4] = {sampled_p, mean_p, max raw weight, #uniform}).  u_a/u_b: injected uniforms."""
+        stats f64 [4] = {sampled_p, mean_p, max raw weight, #uniform}).  u_a/u_b: injected uniforms.
+
+        Sharded replay (Ape-X over G GPUs): when `self.shard_world > 1` this tree is one shard of
+        a G-way replay; each rank draws its B/G share locally, and the importance weights use the GLOBAL
+        sum of priorities / item count / max weight (per_buffer.py:88-94 evaluated over the union of the
+        shards) obtained with two tiny all-reduces (2 x f64 SUM, 1 x f64 MAX)."""
         B = batch_size
         idx = torch.empty(B, dtype=torch.int64, device=self.device)
         w = torch.empty(B, dtype=torch.float64, device=self.device)
         p = torch.empty(B, dtype=torch.float64, device=self.device)
         stats = torch.empty(4, dtype=torch.float64, device=self.device)
         self._sample_ctr += 1
+        sharded = getattr(self, "shard_world", 1) > 1
+        g_total = g_count = None
+        if sharded:
+            import torch.distributed as dist
+            tot = torch.stack([self._tree[0], torch.tensor(float(self.buffer_counter), dtype=torch.float64, device=self.device)])
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            g_total = tot[0:1].contiguous()
+            g_count = tot[1:2].to(torch.int64).contiguous()
         C.jb_per_sample(ptr(self._tree), self.buffer_size, self.buffer_counter, B, float(beta),
-                        float(self.uniform_sample_prob), ptr(u_a), ptr(u_b), self.seed, self._sample_ctr, 0, 0,
-                        ptr(idx), ptr(w), ptr(p), ptr(stats), 1, stream_ptr())
+                        float(self.uniform_sample_prob), ptr(u_a), ptr(u_b), self.seed, self._sample_ctr, ptr(g_total),
+                        ptr(g_count), ptr(idx), ptr(w), ptr(p), ptr(stats), 0 if sharded else 1, stream_ptr())
+        if sharded:
+            import torch.distributed as dist
+            wmax = stats[2:3].clone()
+            dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+            C.jb_per_scale_weights(ptr(w), ptr(wmax), B, stream_ptr())
+            stats[1] = g_total[0] / g_count[0].to(torch.float64)
         transitions = self.gather_device(idx - self.first_leaf_index)
         return transitions, w, idx, stats
 

@@ -30,4 +30,7 @@ def attach(agent, world_size, average_with="avg"):
             flat_grad.div_(world_size)
 
     agent.allreduce = allreduce
+    mem = getattr(agent, "memory", None)
+    if mem is not None and hasattr(mem, "sample_device") and hasattr(mem, "tree_size"):
+        mem.shard_world = world_size            # PER tree becomes one shard of a world_size-way replay
     return agent

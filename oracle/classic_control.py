@@ -91,3 +91,92 @@ class CartPoleBatch:
     @property
     def obs(self):
         return self.phys.astype(np.float32)
+
+
+class PendulumBatch:
+    """gym 0.23.0 Pendulum-v1 (max_speed 8, max_torque 2, dt 0.05, g 10, m = l = 1; 200-step TimeLimit) behind
+    _Gym.step's action rescale ((a+1)/2*(high-low)+low, gym_env.py:41-45).  PARITY UNPINNED (third-party)."""
+    max_speed, max_torque, dt, g, m, l, max_steps = 8.0, 2.0, 0.05, 10.0, 1.0, 1.0, 200
+
+    def __init__(self, n, seed=0, stream_base=0, auto_reset=True):
+        self.n, self.seed, self.stream_base, self.auto_reset = n, seed, stream_base, auto_reset
+        self.ids = np.arange(n, dtype=np.int64)
+        self.phys = np.zeros((n, 2), dtype=np.float64)
+        self.elapsed = np.zeros(n, dtype=np.int32)
+        self.episode = np.zeros(n, dtype=np.int64)
+
+    def _draw(self, mask):
+        u = _reset_uniforms(self.seed, np.uint64(self.stream_base), self.ids[mask], self.episode[mask], 2)
+        self.phys[mask, 0] = -math.pi + (2 * math.pi) * u[0]
+        self.phys[mask, 1] = -1.0 + 2.0 * u[1]
+        self.episode[mask] += 1
+        self.elapsed[mask] = 0
+
+    def _obs(self):
+        th, thdot = self.phys[:, 0], self.phys[:, 1]
+        return np.stack([np.cos(th), np.sin(th), thdot], axis=1).astype(np.float32)
+
+    def reset(self):
+        self._draw(np.ones(self.n, dtype=bool))
+        return self._obs()
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float32).reshape(self.n)
+        scaled = ((a + np.float32(1.0)) / np.float32(2.0)) * np.float32(4.0) + np.float32(-2.0)
+        u = np.clip(scaled.astype(np.float64), -self.max_torque, self.max_torque)
+        th, thdot = self.phys[:, 0].copy(), self.phys[:, 1].copy()
+        an = np.mod(th + math.pi, 2 * math.pi) - math.pi
+        costs = an * an + 0.1 * (thdot * thdot) + 0.001 * (u * u)
+        newthdot = thdot + (3 * self.g / (2 * self.l) * np.sin(th) + 3.0 / (self.m * (self.l * self.l)) * u) * self.dt
+        newthdot = np.clip(newthdot, -self.max_speed, self.max_speed)
+        newth = th + newthdot * self.dt
+        self.phys = np.stack([newth, newthdot], axis=1)
+        self.elapsed += 1
+        done = self.elapsed >= self.max_steps
+        next_obs = self._obs()
+        reward = (-costs).astype(np.float32)
+        if self.auto_reset and done.any():
+            self._draw(done)
+        return next_obs, reward, done
+
+
+class MountainCarBatch:
+    """gym 0.23.0 MountainCar-v0 (200-step TimeLimit).  PARITY UNPINNED (third-party)."""
+    min_position, max_position, max_speed, goal_position, goal_velocity = -1.2, 0.6, 0.07, 0.5, 0.0
+    force, gravity, max_steps = 0.001, 0.0025, 200
+
+    def __init__(self, n, seed=0, stream_base=0, auto_reset=True):
+        self.n, self.seed, self.stream_base, self.auto_reset = n, seed, stream_base, auto_reset
+        self.ids = np.arange(n, dtype=np.int64)
+        self.phys = np.zeros((n, 2), dtype=np.float64)
+        self.elapsed = np.zeros(n, dtype=np.int32)
+        self.episode = np.zeros(n, dtype=np.int64)
+
+    def _draw(self, mask):
+        u = _reset_uniforms(self.seed, np.uint64(self.stream_base), self.ids[mask], self.episode[mask], 2)
+        self.phys[mask, 0] = -0.6 + 0.2 * u[0]
+        self.phys[mask, 1] = 0.0
+        self.episode[mask] += 1
+        self.elapsed[mask] = 0
+
+    def reset(self):
+        self._draw(np.ones(self.n, dtype=bool))
+        return self.phys.astype(np.float32)
+
+    def step(self, action):
+        a = np.asarray(action).reshape(self.n).astype(np.float64)
+        pos, vel = self.phys[:, 0].copy(), self.phys[:, 1].copy()
+        vel = vel + ((a - 1) * self.force + np.cos(3 * pos) * (-self.gravity))
+        vel = np.clip(vel, -self.max_speed, self.max_speed)
+        pos = pos + vel
+        pos = np.clip(pos, self.min_position, self.max_position)
+        vel = np.where((pos == self.min_position) & (vel < 0), 0.0, vel)
+        term = (pos >= self.goal_position) & (vel >= self.goal_velocity)
+        self.phys = np.stack([pos, vel], axis=1)
+        self.elapsed += 1
+        done = term | (self.elapsed >= self.max_steps)
+        next_obs = self.phys.astype(np.float32)
+        reward = np.full(self.n, -1.0, dtype=np.float32)
+        if self.auto_reset and done.any():
+            self._draw(done)
+        return next_obs, reward, done

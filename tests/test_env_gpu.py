@@ -75,3 +75,51 @@ def test_cartpole_time_limit_and_score():
     assert torch.all(d == 1.0) and torch.all(r == -1.0)
     assert torch.all(env.elapsed == 0)
     assert env.stats[0].item() == 4 and env.stats[1].item() == 20.0
+
+
+def _sync(ref, env):
+    ref.phys = env.phys.cpu().numpy().copy()
+    ref.elapsed = env.elapsed.cpu().numpy().copy()
+    ref.episode = env.episode.cpu().numpy().copy()
+
+
+def test_pendulum_matches_oracle():
+    from jorldy_b200.core import Env
+    from oracle.classic_control import PendulumBatch
+    n = 256
+    env = Env("pendulum", num_envs=n, seed=3)
+    ref = PendulumBatch(n, seed=3)
+    obs = env.reset(); robs = ref.reset()
+    assert np.array_equal(env.phys.cpu().numpy(), ref.phys)
+    np.testing.assert_allclose(obs, robs, rtol=0, atol=1e-6)
+    assert env.state_size == 3 and env.action_size == 1 and env.action_type == "continuous"
+    rs = np.random.RandomState(1)
+    for t in range(230):
+        a = rs.uniform(-1, 1, size=(n, 1)).astype(np.float32)
+        _sync(ref, env)
+        ns, r, d = env.step(a)
+        rns, rr, rd = ref.step(a)
+        np.testing.assert_allclose(ns, rns, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(r.reshape(-1), rr, rtol=1e-6, atol=1e-6)
+        assert np.array_equal(d.reshape(-1), rd)
+        np.testing.assert_allclose(env.phys.cpu().numpy(), ref.phys, rtol=0, atol=1e-11)
+
+
+def test_mountain_car_matches_oracle():
+    from jorldy_b200.core import Env
+    from oracle.classic_control import MountainCarBatch
+    n = 256
+    env = Env("mountain_car", num_envs=n, seed=4)
+    ref = MountainCarBatch(n, seed=4)
+    obs = env.reset(); robs = ref.reset()
+    assert np.array_equal(obs, robs)
+    assert env.state_size == 2 and env.action_size == 3
+    rs = np.random.RandomState(2)
+    for t in range(230):
+        a = rs.randint(0, 3, size=(n, 1))
+        _sync(ref, env)
+        ns, r, d = env.step(a)
+        rns, rr, rd = ref.step(a)
+        np.testing.assert_allclose(ns, rns, rtol=0, atol=1e-7)
+        assert np.array_equal(d.reshape(-1), rd) and np.all(r == -1.0)
+        np.testing.assert_allclose(env.phys.cpu().numpy(), ref.phys, rtol=0, atol=1e-14)
