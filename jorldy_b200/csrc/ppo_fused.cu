@@ -56,8 +56,7 @@ __device__ __forceinline__ void cp_commit_wait() {
 
 // ---- grid barrier (all CTAs co-resident: cooperative launch) ------------------------------------------
 __device__ __forceinline__ void grid_bar(unsigned int* ctr, unsigned int& epoch, unsigned int nctas) {
-  __threadfence();                       // each thread's phase writes are ordered gpu-wide before it arrives
-  __syncthreads();
+  __syncthreads();                       // CTA scope: every thread's phase writes happen-before thread 0's release
   if (threadIdx.x == 0) {
     epoch += 1;
     const unsigned int target = epoch * nctas;
