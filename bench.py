@@ -330,8 +330,16 @@ def main():
                 "last_result": res}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # NCCL ops captured inside CUDA graphs make destroy_process_group() hang: drop the graphs, meet at a
+        # barrier, flush, and leave without the collective teardown.
+        agent._graphs.clear()
+        col._graph = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_e2e(np, torch, Agent, Env, dev, rank=0, world=1, steps=2):

@@ -72,6 +72,9 @@ JB_API int jb_gemm(const float* A, int lda, int a_kc, const float* B, int ldb, i
                    float* rowsum_a, int accumulate, void* stream);
 JB_API int jb_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int in_f, int out_f,
                          int relu, void* stream);
+/* tcgen05 / TMEM 3xTF32 forward for large M (M % 128 == 0, out_f % 128 == 0, in_f % 32 == 0); -22 otherwise */
+JB_API int jb_linear_fwd_tc(const float* x, const float* w, const float* b, float* y, int M, int in_f, int out_f,
+                            int relu, void* stream);
 JB_API int jb_linear_bwd_dx(const float* dy, const float* w, float* dx, int M, int in_f, int out_f,
                             const float* relu_act, void* stream);
 JB_API int jb_linear_bwd_dw(const float* dy, const float* x, float* dw, float* db, int M, int in_f, int out_f,

@@ -147,7 +147,7 @@ class PPO(BaseAgent):
 
     def _graph_for(self, st, B):
         """CUDA graph of GRAPH_CHUNK minibatch steps reading indices through the device cursor."""
-        key = (B, st["state"].data_ptr(), st["adv"].data_ptr())
+        key = (B, st["state"].data_ptr(), st["action"].data_ptr(), st["adv"].data_ptr())
         g = self._graphs.get(key)
         if g is not None:
             return g
@@ -225,6 +225,7 @@ class PPO(BaseAgent):
 
         # ---- optimisation epochs (ppo.py:114-175) ----
         B = self.batch_size
+        self.optimizer._sync_lr()          # graph replays do not pass through optimizer.step()'s host-side lr check
         self._acc.zero_()
         self._acc[3] = -float("inf")
         self._acc[4] = float("inf")
@@ -283,12 +284,23 @@ class PPO(BaseAgent):
         batched = len(buf) > 0 and np.shape(buf[0]["reward"])[0] > 1
         tr = self.memory.sample_batched() if batched else self.memory.sample()
         dev = self.device
-        state = torch.as_tensor(tr["state"], dtype=torch.float32, device=dev).reshape(len(tr["reward"]), -1)
-        next_state = torch.as_tensor(tr["next_state"], dtype=torch.float32, device=dev).reshape(len(tr["reward"]), -1)
-        reward = torch.as_tensor(tr["reward"], dtype=torch.float32, device=dev).reshape(-1)
-        done = torch.as_tensor(tr["done"], dtype=torch.float32, device=dev).reshape(-1)
-        action = self._action_to_device(tr["action"])
-        return self._learn_tensors(state, action, reward, done, next_state=next_state)
+        n = len(tr["reward"])
+        # host transitions land in PERSISTENT device buffers: captured CUDA graphs bake these pointers
+        hin = getattr(self, "_host_in", None)
+        if hin is None or hin["n"] != n:
+            hin = {"n": n,
+                   "state": torch.empty(n, int(np.prod(np.shape(tr["state"])[1:])), device=dev),
+                   "next_state": torch.empty(n, int(np.prod(np.shape(tr["state"])[1:])), device=dev),
+                   "reward": torch.empty(n, device=dev), "done": torch.empty(n, device=dev),
+                   "action": (torch.empty(n, self.action_size, device=dev) if self.continuous
+                              else torch.empty(n, dtype=torch.int32, device=dev))}
+            self._host_in = hin
+        hin["state"].copy_(torch.as_tensor(tr["state"], dtype=torch.float32, device=dev).reshape(n, -1))
+        hin["next_state"].copy_(torch.as_tensor(tr["next_state"], dtype=torch.float32, device=dev).reshape(n, -1))
+        hin["reward"].copy_(torch.as_tensor(tr["reward"], dtype=torch.float32, device=dev).reshape(-1))
+        hin["done"].copy_(torch.as_tensor(tr["done"], dtype=torch.float32, device=dev).reshape(-1))
+        hin["action"].copy_(self._action_to_device(tr["action"]))
+        return self._learn_tensors(hin["state"], hin["action"], hin["reward"], hin["done"], next_state=hin["next_state"])
 
     def learn_rollout(self, rollout):
         """Resident path: `rollout` is a DeviceRollout filled by the batched collect loop."""

@@ -2,9 +2,21 @@
 from ..dev import C, ptr, stream_ptr
 
 
+import os
+
+TC_MIN_ROWS = 1024     # below this a 128x128 tile grid cannot fill the 148 SMs: stay on the fp32 FFMA tiles
+_USE_TC = os.environ.get("JB_NO_TC", "0") != "1"
+
+
 def linear_fwd(x, w, b, y, relu):
+    """y = act(x W^T + b).  Large-M products (env-row batches) go to the tcgen05/TMEM 3xTF32 kernel
+    (csrc/tc_gemm.cu); minibatch-sized ones to the fp32 FFMA tiles (csrc/linear.cu)."""
     M, in_f = x.shape
-    C.jb_linear_fwd(ptr(x), ptr(w), ptr(b), ptr(y), M, in_f, w.shape[0], int(relu), stream_ptr())
+    out_f = w.shape[0]
+    if _USE_TC and M >= TC_MIN_ROWS and M % 128 == 0 and out_f % 128 == 0 and in_f % 32 == 0 and b is not None:
+        C.jb_linear_fwd_tc(ptr(x), ptr(w), ptr(b), ptr(y), M, in_f, out_f, int(relu), stream_ptr())
+        return
+    C.jb_linear_fwd(ptr(x), ptr(w), ptr(b), ptr(y), M, in_f, out_f, int(relu), stream_ptr())
 
 
 def linear_bwd_dx(dy, w, dx, relu_act=None, accumulate=False):
