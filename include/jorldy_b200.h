@@ -138,6 +138,9 @@ JB_API int jb_nchw_to_nhwc(const float* x, int B, int P, int C, const float* rel
 JB_API int jb_ppo_fused_args_size(void);
 JB_API int jb_ppo_fused_max_ctas(void);
 JB_API int jb_ppo_fused_run(const void* host_args, void* stream);
+/* Debug aid: clock64 stamps of the last step of the previous run made with JB_FUSED_SKIP=256 in the
+ * environment; host_out receives 256 x 32 long longs. */
+JB_API int jb_ppo_fused_trace(long long* host_out);
 
 /* ---------------------------------------------------------------------------------------------
  * Value-based learners — jorldy/core/agent/dqn.py:99-138, double.py:25-41, multistep.py:41-50,

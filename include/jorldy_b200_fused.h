@@ -19,14 +19,17 @@ typedef struct jb_ppo_fused_args {
   const float *adv, *ret, *vold, *logp_old;
   const int32_t *perm;               /* [>= (cursor + n_steps) * B] shuffled row ids */
   /* workspaces */
-  float *h1, *h2;                    /* [B, H] */
+  float *h1;                         /* [H/32, B, 32] tiled layer-1 activations */
+  float *h2;                         /* [B, H] layer-2 activations, row major */
   float *xg;                         /* [B, D] */
-  float *dh1;                        /* [B, H] */
-  float *rowbuf;                     /* [B, 24] */
+  float *w1p;                        /* [B/32, H, D+1] per-row-tile partial dW1 | db1 */
+  float *headp;                      /* [H/32, 2, B, 4] per-column-tile partial head outputs */
+  float *h2t;                        /* [H/32, B, 32] tiled copy of h2 */
+  float *W2t;                        /* [H/32, H, 32] tiled shadow of W2 (maintained by the Adam phase) */
   float *partials;                   /* [256] per-CTA squared-norm partials */
   float *acc;                        /* [8] learn()-level statistic accumulators */
   int32_t *cur_idx;                  /* [B] */
-  unsigned int *barrier;             /* [1] grid-barrier counter (zeroed by the launcher) */
+  unsigned int *barrier;             /* [64] grid-barrier counter + per-column-tile job counters (zeroed by the launcher) */
   long long *step;                   /* Adam step counter (device) */
   long long *cursor;                 /* minibatch cursor (device) */
   const float *lr;                   /* learning rate (device scalar) */

@@ -15,7 +15,7 @@ class FusedArgs(ctypes.Structure):
         ("gW1", _P), ("gb1", _P), ("gW2", _P), ("gb2", _P), ("gWh", _P * 3), ("gbh", _P * 3),
         ("flat", _P), ("grad", _P), ("am", _P), ("av", _P), ("P4", ctypes.c_longlong),
         ("state", _P), ("action", _P), ("adv", _P), ("ret", _P), ("vold", _P), ("logp_old", _P), ("perm", _P),
-        ("h1", _P), ("h2", _P), ("xg", _P), ("dh1", _P), ("rowbuf", _P), ("partials", _P), ("acc", _P),
+        ("h1", _P), ("h2", _P), ("xg", _P), ("w1p", _P), ("headp", _P), ("h2t", _P), ("W2t", _P), ("partials", _P), ("acc", _P),
         ("cur_idx", _P), ("barrier", _P), ("step", _P), ("cursor", _P), ("lr", _P),
         ("nh", ctypes.c_int * 3),
         ("B", ctypes.c_int), ("D", ctypes.c_int), ("H", ctypes.c_int), ("A", ctypes.c_int), ("nout", ctypes.c_int),
@@ -29,7 +29,7 @@ def supported(agent, B):
     net = agent.network
     head = getattr(net, "head", None)
     return (getattr(head, "kind", None) == "mlp" and type(agent.optimizer).__name__ == "Adam" and agent.allreduce is None
-            and B % 32 == 0 and net.D_hidden % 32 == 0 and net.D_hidden <= 512 and head.D_in <= 16 and net.nout <= 8
+            and B % 32 == 0 and B <= 512 and net.D_hidden % 32 == 0 and net.D_hidden <= 512 and head.D_in <= 16 and net.nout <= 8
             and head.D_head_out == net.D_hidden and agent.action_size <= 8)
 
 
@@ -41,9 +41,10 @@ class FusedRunner:
         H, D = net.D_hidden, net.head.D_in
         self.ws = {
             "h1": torch.empty(B, H, device=dev), "h2": torch.empty(B, H, device=dev), "xg": torch.empty(B, D, device=dev),
-            "dh1": torch.empty(B, H, device=dev), "rowbuf": torch.zeros(B, 24, device=dev),
+            "w1p": torch.zeros(B // 32, H, D + 1, device=dev), "headp": torch.zeros(H // 32, 2, B, 4, device=dev),
+            "h2t": torch.empty(H // 32, B, 32, device=dev), "W2t": torch.empty(H // 32, H, 32, device=dev),
             "partials": torch.zeros(256, device=dev), "cur_idx": torch.zeros(B, dtype=torch.int32, device=dev),
-            "barrier": torch.zeros(4, dtype=torch.int32, device=dev),
+            "barrier": torch.zeros(64, dtype=torch.int32, device=dev),
         }
         self.max_ctas = C.jb_ppo_fused_max_ctas()
 
@@ -69,7 +70,8 @@ class FusedRunner:
         a.state, a.action = ptr(st["state"]), ptr(st["action"])
         a.adv, a.ret, a.vold, a.logp_old, a.perm = ptr(st["adv"]), ptr(st["ret"]), ptr(st["value"]), ptr(st["logp_old"]), ptr(st["perm"])
         ws = self.ws
-        a.h1, a.h2, a.xg, a.dh1, a.rowbuf = ptr(ws["h1"]), ptr(ws["h2"]), ptr(ws["xg"]), ptr(ws["dh1"]), ptr(ws["rowbuf"])
+        a.h1, a.h2, a.xg, a.w1p, a.headp = ptr(ws["h1"]), ptr(ws["h2"]), ptr(ws["xg"]), ptr(ws["w1p"]), ptr(ws["headp"])
+        a.h2t, a.W2t = ptr(ws["h2t"]), ptr(ws["W2t"])
         a.partials, a.acc, a.cur_idx, a.barrier = ptr(ws["partials"]), ptr(ag._acc), ptr(ws["cur_idx"]), ptr(ws["barrier"])
         a.step, a.cursor, a.lr = ptr(opt._step_dev), ptr(ag._cursor), ptr(opt._lr_dev)
         a.B, a.D, a.H, a.A, a.nout = self.B, net.head.D_in, net.D_hidden, ag.action_size, net.nout

@@ -3,29 +3,37 @@
 //
 // Why: at the reference's minibatch size (256 x [4-512-512-(A+1)]) one step is ~0.4 GFLOP and < 4 MB of
 // traffic, i.e. microseconds of work, and one learn() is n_epoch * N*T/B = 6144 strictly sequential
-// steps.  As 13 separate launches per step (round-1 "graph" path) each step cost 71 us, almost all of
-// it launch gaps and cold per-kernel load latency (profiles/r01_launches_ppo_summary.md).  Here one
-// CTA per SM stays resident for the whole epoch, phases are separated by a hand-rolled grid barrier
-// (one atomic + spin, ~1 us), and producer/consumer fusion removes intermediate tensors:
+// steps.  As 13 separate launches per step (the "graph" path) each step cost 71 us, almost all of it
+// launch gaps and cold per-kernel load latency (profiles/r01_launches_ppo_summary.md).  Here one CTA per
+// SM stays resident for the whole epoch and a step is THREE phases separated by a hand-rolled grid
+// barrier (~1.3 us each; scripts/bench_gridbar.cu compares the variants):
 //
-//   P1  layer-2 forward tiles (32x32, fp32 FFMA, k split 4 ways in-CTA).  The A panel h1 =
-//       relu(x W1^T + b1) is GENERATED in shared memory from the gathered state rows (K = D <= 16), never
-//       read from HBM; the W2 panel arrives by cp.async.cg.  Column-tile-0 CTAs also publish h1 / xg.
-//   P2  one warp per row: narrow heads + the whole loss row math (shared with ppo.cu through
-//       ppo_rowmath.cuh): d loss/d logits, the two candidate value gradients, per-row statistics.
-//   P3  backward tiles.  dh2 = (dout Wh) * relu'(h2) is GENERATED on the fly into the A panel of
-//       both products that consume it — dW2 = dh2^T h1 (+ db2 as the panel row-sum) and
-//       dh1 = (dh2 W2) * relu'(h1) — plus the head weight gradients.  Every job folds its tile's sum of
-//       squares into a per-CTA accumulator (global-norm clipping needs ||g|| before any update).
-//   P4  dW1 / db1 column jobs, learn()-level statistics (CTA 0), publish the per-CTA norm partials.
-//   P5  Adam on a static 1/gridDim slice of the flat parameter buffer, clip coefficient from the
-//       fixed-order fold of the partials.
+//   P1  layer-2 forward tiles (32x32, fp32 FFMA, 16-way in-CTA split-K).  The A panel h1 = relu(x W1^T + b1)
+//       is GENERATED in shared memory from the gathered state rows (K = D <= 16), never read from HBM; the
+//       W2 panel arrives by cp.async.cg.  The epilogue also emits, per tile, the PARTIAL head outputs
+//       sum_{n in tile} h2[m, n] Wh[o, n], so that nobody has to re-read h2 rows to evaluate the heads.
+//   P3  row phase + backward.  Every CTA redundantly folds the partial head outputs of every minibatch
+//       row and runs the whole loss row math (ppo_rowmath.cuh, one thread per row): d loss/d head outputs
+//       of the minibatch end up in shared memory without a phase of their own (256 rows of ~300
+//       instructions cost less than a barrier).  Then the backward jobs, each with its panels prefetched
+//       while the previous job reduces:
+//         JB  dh1 tile = ((dout Wh) * relu'(h2)) W2, masked by relu'(h1); dh2 is generated in place in the
+//             A panel; the epilogue turns the tile into PARTIAL dW1/db1 (x rows are <= 64 B each), so dh1
+//             never leaves the SM.
+//         JA  a PAIR of dW2 tiles sharing one generated dh2 panel (+ db2 as the panel row-sum).
+//         JC  head weight / bias gradients, 32 columns per job.
+//         JD  fixed-order fold of the MT partial dW1/db1 (waits on a per-column-tile completion counter
+//             that the JB jobs bump — every CTA runs its JB jobs first, so the wait cannot deadlock).
+//       Every job adds its outputs' squares to a per-thread accumulator; one block reduction per step
+//       publishes the CTA's share of ||g||^2.
+//   P5  Adam on a static 1/gridDim slice of the flat parameter buffer; p/m/v of the slice are loaded into
+//       registers BEFORE the barrier, the clip coefficient comes from a fixed-order fold of the partials.
 //
 // Determinism: static job -> CTA maps, fixed-order reductions, no float atomics: bit-reproducible run
 // to run.  Coherence: every buffer written inside the kernel is read with ld.global.cg / cp.async.cg
-// (L2), and the barrier's gpu-scope fences order the phases.
-// Constraints (else the host uses the multi-launch path): B % 32 == 0, H % 32 == 0, H <= 512, D <= 16,
-// nout <= 8, single GPU (no gradient all-reduce between backward and Adam).
+// (L2), and the barrier's gpu-scope release/acquire orders the phases.
+// Constraints (else the host uses the multi-launch path): B % 32 == 0, B <= 512, H % 32 == 0, H <= 512,
+// D <= 16, nout <= 8, single GPU (no gradient all-reduce between backward and Adam).
 #include <cstdlib>
 #include "common.cuh"
 #include "ppo_rowmath.cuh"
@@ -37,22 +45,61 @@ constexpr int NT = 256;
 constexpr int PK = 512;
 constexpr int MAXD = 16;
 constexpr int MAXO = 8;
-constexpr int ROWBUF = 24;          // floats per row: dpol[16] dv1 dv2 sq1 sq2 surr_min ent ratio pmin
-constexpr int SMALL_FLOATS = 2048;  // xs[32*16], ds[32*8], reduction scratch
-constexpr int PANEL_FLOATS = PK * 36;   // >= 32 * (PK + 4)
+constexpr int KG = 16;                                  // in-CTA split-K groups
+constexpr int SMALL_FLOATS = 2048;                      // xs[32*16], reduction scratch, row ids
+constexpr int RED_FLOATS = KG * (32 * 36 + 16);         // 18688: split-K fold area; also >= a 32x(PK+4) or PKx36 panel
+constexpr int JA_ROWS = 256;                            // minibatch rows per dW2 / head-gradient panel
+constexpr int R2_FLOATS = JA_ROWS * 32;                 // 8192: a dense [256][32] panel
+constexpr int MAX_B = 512;                              // minibatch rows (row-phase scratch in s_small)
+constexpr int ADAM_IT = 8;                              // float4 per thread kept in registers across the barrier
+constexpr int CTR_JB = 32;                              // a.barrier[CTR_JB + kt]: finished JB jobs of column tile kt
 
 typedef jb_ppo_fused_args Args;
 
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-__device__ __forceinline__ void cp16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void cp_commit_wait() {
-  asm volatile("cp.async.commit_group;\n" ::);
-  asm volatile("cp.async.wait_group 0;\n" ::);
-}
+// ---- panel staging: TMA 1-D bulk copies (cp.async.bulk, one request per panel row) completing on one
+// mbarrier.  (The first versions issued 16-byte cp.async per thread: 4-8 K LDGSTS per panel fill the SM's
+// load queue, so "prefetching" stalled the issuing warps for as long as the transfer took and every
+// ordinary load behind them waited too.  A bulk request costs one instruction per 128 B - 2 KB row and
+// the copy engine does the rest.)  Exactly one group of copies is in flight at a time: `Stager` tracks
+// the bytes of the group being issued and the phase parity of the barrier.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+struct Stager {
+  unsigned mbar;      // shared-space address of the mbarrier
+  unsigned bytes;     // bytes issued in the open group (uniform across the CTA)
+  unsigned parity;    // phase parity the next wait() completes on
+  __device__ __forceinline__ void init(void* bar) {
+    mbar = smem_u32(bar); bytes = 0; parity = 0;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+  }
+  __device__ __forceinline__ void copy(void* dst, const void* src, unsigned nbytes) const {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(nbytes), "r"(mbar) : "memory");
+  }
+  __device__ __forceinline__ void commit() {
+    if (bytes && threadIdx.x == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+    bytes = 0;
+  }
+  __device__ __forceinline__ void wait() {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(mbar), "r"(parity)
+        : "memory");
+    parity ^= 1u;
+  }
+};
 
 // ---- grid barrier (all CTAs co-resident: cooperative launch) ------------------------------------------
 __device__ __forceinline__ void grid_bar(unsigned int* ctr, unsigned int& epoch, unsigned int nctas) {
@@ -63,29 +110,27 @@ __device__ __forceinline__ void grid_bar(unsigned int* ctr, unsigned int& epoch,
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(ctr) : "memory");
     unsigned int v;
     do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(ctr) : "memory");
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(ctr) : "memory");
     } while (v < target);
-    __threadfence();
+    asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+    asm volatile("fence.proxy.async;\n" ::: "memory");   // other SMs' generic-proxy writes before this SM's bulk copies
   }
   __syncthreads();
 }
 
-// ---- panel staging ---------------------------------------------------------------------------------
-// KC: sm[r*(kp+4) + k] = G[(r0+r)*ld + k0 + k], r < 32, k < kp
-__device__ __forceinline__ void stage_kc(float* sm, const float* G, int ld, int r0, int k0, int kp) {
-  const int c16s = kp >> 2, total = 32 * c16s, stride = kp + 4;
-  for (int e = threadIdx.x; e < total; e += NT) {
-    const int row = e / c16s, c = e - row * c16s;
-    cp16(&sm[row * stride + c * 4], &G[(size_t)(r0 + row) * ld + k0 + c * 4]);
+// k-contiguous panel with padded rows: sm[r*(kp+4) + k] = G[(r0+r)*ld + k0 + k], r < 32, k < kp
+// (32 requests of kp*4 bytes, one lane of every 8)
+__device__ __forceinline__ void stage_kc(Stager& st, float* sm, const float* G, int ld, int r0, int k0, int kp) {
+  if ((threadIdx.x & 7) == 0) {
+    const int row = threadIdx.x >> 3;
+    st.copy(&sm[row * (kp + 4)], &G[(size_t)(r0 + row) * ld + k0], (unsigned)kp * 4u);
   }
+  st.bytes += 32u * (unsigned)kp * 4u;
 }
-// nonKC: sm[k*36 + c] = G[(k0+k)*ld + r0 + c], k < kp, c < 32
-__device__ __forceinline__ void stage_nonkc(float* sm, const float* G, int ld, int r0, int k0, int kp) {
-  const int total = kp * 8;
-  for (int e = threadIdx.x; e < total; e += NT) {
-    const int k = e >> 3, c = e & 7;
-    cp16(&sm[k * 36 + c * 4], &G[(size_t)(k0 + k) * ld + r0 + c * 4]);
-  }
+// dense [rows][32] panel that is ONE contiguous block in global memory (the tiled h1t / h2t / W2t layouts)
+__device__ __forceinline__ void stage_block(Stager& st, float* sm, const float* G, int rows) {
+  if (threadIdx.x == 0) st.copy(sm, G, (unsigned)rows * 128u);
+  st.bytes += (unsigned)rows * 128u;
 }
 
 // ---- 32x32 tile product over a staged panel ----------------------------------------------------------
@@ -93,8 +138,8 @@ __device__ __forceinline__ void stage_nonkc(float* sm, const float* G, int ld, i
 // 256 FFMA.  (The first version used 4 k-groups x 4x4 micro-tiles = 8 LDS.128 per 64 FFMA; every LDS.128
 // costs 4 shared-memory phases whatever the broadcast pattern, so that shape was shared-memory-bandwidth
 // bound at <= 50 % of the FFMA rate.)  Rows/cols are interleaved (r = ty + 4 i) for k-contiguous panels so
-// a quarter-warp's 16-byte reads fall in distinct banks, contiguous (r = 8 ty + i) for [k][32] panels.
-constexpr int KG = 16;
+// a quarter-warp's 16-byte reads fall in distinct banks, contiguous (r = 8 ty + i) for dense [k][32] panels
+// (no padding needed there: the 8 lanes of one LDS.128 phase read at most 4 distinct 32-byte spans of one row).
 template <bool A_KC, bool B_KC>
 __device__ __forceinline__ void tile_mma(const float* As, const float* Bs, int kp, float (&acc)[8][8], float* rs) {
   const int tid = threadIdx.x, grp = tid >> 4, t = tid & 15, tx = t & 3, ty = t >> 2;
@@ -110,8 +155,8 @@ __device__ __forceinline__ void tile_mma(const float* As, const float* Bs, int k
     } else {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 v0 = *reinterpret_cast<const float4*>(&As[(k + q) * 36 + ty * 8]);
-        const float4 v1 = *reinterpret_cast<const float4*>(&As[(k + q) * 36 + ty * 8 + 4]);
+        const float4 v0 = *reinterpret_cast<const float4*>(&As[(k + q) * 32 + ty * 8]);
+        const float4 v1 = *reinterpret_cast<const float4*>(&As[(k + q) * 32 + ty * 8 + 4]);
         a[0][q] = v0.x; a[1][q] = v0.y; a[2][q] = v0.z; a[3][q] = v0.w;
         a[4][q] = v1.x; a[5][q] = v1.y; a[6][q] = v1.z; a[7][q] = v1.w;
       }
@@ -125,8 +170,8 @@ __device__ __forceinline__ void tile_mma(const float* As, const float* Bs, int k
     } else {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 v0 = *reinterpret_cast<const float4*>(&Bs[(k + q) * 36 + tx * 8]);
-        const float4 v1 = *reinterpret_cast<const float4*>(&Bs[(k + q) * 36 + tx * 8 + 4]);
+        const float4 v0 = *reinterpret_cast<const float4*>(&Bs[(k + q) * 32 + tx * 8]);
+        const float4 v1 = *reinterpret_cast<const float4*>(&Bs[(k + q) * 32 + tx * 8 + 4]);
         b[0][q] = v0.x; b[1][q] = v0.y; b[2][q] = v0.z; b[3][q] = v0.w;
         b[4][q] = v1.x; b[5][q] = v1.y; b[6][q] = v1.z; b[7][q] = v1.w;
       }
@@ -148,9 +193,9 @@ template <bool A_KC>
 __device__ __forceinline__ int tile_row(int ty, int i) { return A_KC ? (ty + 4 * i) : (ty * 8 + i); }
 
 // fold the 16 k-groups in a fixed order; thread gets outputs e = tid + r*256 -> (m = e>>5, n = e&31).
-// `red` (16 x (32*36 + 16) floats = 75 KB) aliases the dead A panel and the head of the dead B panel.
-// Layout: row stride 36, odd groups shifted by 16 banks, columns rotated by 4*(m>>3) for [k][32] A panels:
-// the 64 partial-tile stores of a warp are conflict-free (k-contiguous panels) or at most 2-way.
+// Layout of `red` (RED_FLOATS): row stride 36, odd groups shifted by 16 banks, columns rotated by 4*(m>>3)
+// for [k][32] A panels: the 64 partial-tile stores of a warp are conflict-free (k-contiguous panels) or
+// at most 2-way.  The caller has synchronised the CTA since the last read of the memory behind `red`.
 template <bool A_KC>
 __device__ __forceinline__ int red_index(int grp, int m, int n) {
   const int rot = A_KC ? 0 : 4 * (m >> 3);
@@ -159,7 +204,6 @@ __device__ __forceinline__ int red_index(int grp, int m, int n) {
 template <bool A_KC, bool B_KC>
 __device__ __forceinline__ void tile_reduce(const float (&acc)[8][8], float* red, float (&outv)[4]) {
   const int tid = threadIdx.x, grp = tid >> 4, t = tid & 15, tx = t & 3, ty = t >> 2;
-  __syncthreads();
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -177,303 +221,449 @@ __device__ __forceinline__ void tile_reduce(const float (&acc)[8][8], float* red
   __syncthreads();
 }
 
-// fixed-order block sum of one float (all threads call; result valid in thread 0 only)
-__device__ __forceinline__ float block_sum0(float v, float* scratch /*[8]*/) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+// fixed-order block sum of one float (all threads call; every thread gets the result)
+__device__ __forceinline__ float block_sum(float v, float* scratch /*[8]*/) {
+  v = jb_warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
   __syncthreads();
   float t = 0.f;
-  if (threadIdx.x == 0) for (int w = 0; w < NT / 32; ++w) t += scratch[w];
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) t += scratch[w];
   return t;
 }
 
+// d (loss) / d (h2 pre-activation) for 4 adjacent columns of one row: (dout[row] . Wh[:, c..c+3]) * relu'(h2)
+__device__ __forceinline__ float4 dh2_quad(const float* drow, const float4 (&wr)[MAXO], float4 hv) {
+  const float4 d0 = *reinterpret_cast<const float4*>(drow);
+  const float4 d1 = *reinterpret_cast<const float4*>(drow + 4);
+  const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+  float4 t = make_float4(d[0] * wr[0].x, d[0] * wr[0].y, d[0] * wr[0].z, d[0] * wr[0].w);
+#pragma unroll
+  for (int o = 1; o < MAXO; ++o) {
+    t.x = fmaf(d[o], wr[o].x, t.x); t.y = fmaf(d[o], wr[o].y, t.y); t.z = fmaf(d[o], wr[o].z, t.z); t.w = fmaf(d[o], wr[o].w, t.w);
+  }
+  return make_float4(hv.x > 0.f ? t.x : 0.f, hv.y > 0.f ? t.y : 0.f, hv.z > 0.f ? t.z : 0.f, hv.w > 0.f ? t.w : 0.f);
+}
+
+// timing trace (debug; JB_FUSED_SKIP bit 8): clock64 at fixed points of the LAST step, per CTA, 32 slots
+__device__ long long g_trace[256 * 32];
+#define TR(i) do { if (trace && tid == 0) g_trace[cta * 32 + (i)] = clock64(); } while (0)
+
 struct HeadTab { const float* w[MAXO]; const float* b[MAXO]; float* gw[MAXO]; float* gb[MAXO]; };
 
-__global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats, int skip /* debug: phase bitmask to skip (timing only) */) {
+__global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats, int flags /* debug: bit 8 = trace */) {
   extern __shared__ __align__(16) float smem[];
   float* s_small = smem;                       // SMALL_FLOATS
-  float* dsm = smem + SMALL_FLOATS;            // resolved d loss/d head-outputs [B][MAXO] (P3) / reduction scratch (P4)
-  float* As = dsm + dsm_floats;                // PANEL_FLOATS
-  float* Bs = As + PANEL_FLOATS;               // PANEL_FLOATS
-  float* xs = s_small;                         // [32][MAXD]
+  float* dsm = smem + SMALL_FLOATS;            // d loss/d head-outputs of the whole minibatch [B][MAXO]
+  float* R0 = dsm + dsm_floats;                // RED_FLOATS: A panels of P1 / JB, split-K fold area, job scratch
+  float* R1 = R0 + RED_FLOATS;                 // RED_FLOATS: B panels
+  float* R2 = R1 + RED_FLOATS;                 // R2_FLOATS:  A panel of JA / JC
+  float* xs = s_small;                         // [32][MAXD] state rows of the current tile (zero padded)
   float* scr = s_small + 768;                  // reduction scratch [128]
-  int* sidx = reinterpret_cast<int*>(s_small + 1024);   // [32] gathered rollout row ids of the tile
+  int* sidx = reinterpret_cast<int*>(s_small + 1024);   // [32] gathered rollout row ids of the P1 tile
+  Stager st;
+  st.init(s_small + 1056);                     // 8-byte mbarrier
+  float* dvs = s_small + 1088;                 // [MAX_B] second candidate value-head gradient of every row
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned int nctas = gridDim.x;
   const int cta = blockIdx.x;
   const int B = a.B, D = a.D, H = a.H, A = a.A, nout = a.nout;
   const int npol = a.continuous ? 2 * A : A;
+  const int nq = (nout + 3) >> 2;              // float4 quads of head outputs per row
   const float invB = 1.0f / (float)B;
   const jbppo::HP hp{a.eps_clip, a.vf_coef, a.ent_coef};
   unsigned int epoch = 0;
-  float cta_norm = 0.f;                        // thread 0 only
   const long long step0 = *a.step, cursor0 = *a.cursor;
   const float lr = *a.lr;
 
-  HeadTab ht;
-  {
+  HeadTab& ht = *reinterpret_cast<HeadTab*>(s_small + 896);   // 32 pointers: shared memory, not 64 live registers
+  if (tid == 0) {
     int o = 0;
-#pragma unroll
     for (int g = 0; g < 3; ++g)
       for (int q = 0; q < a.nh[g]; ++q, ++o) {
-#pragma unroll
-        for (int u = 0; u < MAXO; ++u)
-          if (u == o) { ht.w[u] = a.Wh[g] + (size_t)q * H; ht.b[u] = a.bh[g] + q; ht.gw[u] = a.gWh[g] + (size_t)q * H; ht.gb[u] = a.gbh[g] + q; }
+        ht.w[o] = a.Wh[g] + (size_t)q * H; ht.b[o] = a.bh[g] + q; ht.gw[o] = a.gWh[g] + (size_t)q * H; ht.gb[o] = a.gbh[g] + q;
       }
-#pragma unroll
-    for (int u = 0; u < MAXO; ++u)
-      if (u >= o) { ht.w[u] = a.Wh[0]; ht.b[u] = a.bh[0]; ht.gw[u] = a.gWh[0]; ht.gb[u] = a.gbh[0]; }
+    for (; o < MAXO; ++o) { ht.w[o] = a.Wh[0]; ht.b[o] = a.bh[0]; ht.gw[o] = a.gWh[0]; ht.gb[o] = a.gbh[0]; }
   }
+  __syncthreads();
 
-  const int MT = B / 32, NTL = H / 32;
+  const int MT = B / 32, NTL = H / 32, NP = (NTL + 1) >> 1;
+  const int nJ1 = MT * NTL;          // P1 tiles
+  const int nJB = MT * NTL;          // dh1 tiles (same decomposition as P1: job -> (mt, kt))
+  const int nJA = NTL * NP;          // pairs of dW2 tiles
+  const int nJC = NTL;               // head weight-gradient column jobs
+  const int nJD = NTL;               // dW1 / db1 folds
+  const int nJ3 = nJB + nJA + nJC + nJD;
+  const bool single = B <= JA_ROWS;  // one panel covers the minibatch: JA pairs share their generated panel
+
+  // Adam: static slice of the flat buffers; bias-correction powers advance by one multiply per step
+  const long long per = (a.P4 + nctas - 1) / nctas;
+  const long long lo = (long long)cta * per, hi = min(a.P4, lo + per);
+  float4* p4 = reinterpret_cast<float4*>(a.flat);
+  const float4* g4 = reinterpret_cast<const float4*>(a.grad);
+  float4* m4 = reinterpret_cast<float4*>(a.am);
+  float4* v4 = reinterpret_cast<float4*>(a.av);
+  double pw1 = pow((double)a.beta1, (double)(step0 + 1)), pw2 = pow((double)a.beta2, (double)(step0 + 1));
+  // W2t: tiled shadow of W2 ([H/32][H][32]: W2t[kt][n][c] = W2[n][32 kt + c]) so that the B panel of a JB job is
+  // one contiguous 64 KB block; the owner of a float4 of W2 in the Adam phase also writes its shadow
+  const long long w2_lo = (long long)(a.W2 - a.flat) >> 2, w2_hi = w2_lo + (long long)H * H / 4;
+  auto shadow = [&](long long i, float4 v) {
+    if (i >= w2_lo && i < w2_hi) {
+      const int e = (int)(i - w2_lo) * 4, n = e / H, k = e - n * H;
+      *reinterpret_cast<float4*>(&a.W2t[((size_t)(k >> 5) * H + n) * 32 + (k & 31)]) = v;
+    }
+  };
+  for (long long i = lo + tid; i < hi; i += NT) shadow(i, p4[i]);   // published by the first grid barrier
+  const float one_m_b1 = 1.f - a.beta1, one_m_b2 = 1.f - a.beta2;
+
+  auto issue_stage = [&](int job) {          // first-panel cp.async of a backward job (JD has none)
+    if (job < nJB) {
+      const int mt = job / NTL, kt = job - mt * NTL;
+      stage_kc(st, R0, a.h2, H, mt * 32, 0, H);
+      stage_block(st, R1, a.W2t + (size_t)kt * H * 32, H);
+    } else if (job < nJB + nJA) {
+      const int j = job - nJB, nt = j / NP, kt0 = 2 * (j - nt * NP), kp = min(JA_ROWS, B);
+      stage_block(st, R2, a.h2t + (size_t)nt * B * 32, kp);
+      stage_block(st, R1, a.h1 + (size_t)kt0 * B * 32, kp);
+      if (single && kt0 + 1 < NTL) stage_block(st, R1 + R2_FLOATS, a.h1 + (size_t)(kt0 + 1) * B * 32, kp);
+    } else if (job < nJB + nJA + nJC) {
+      stage_block(st, R2, a.h2t + (size_t)(job - nJB - nJA) * B * 32, min(JA_ROWS, B));
+    }
+    st.commit();
+  };
+  // may the panels of `job` be fetched while the previous job still folds in R0?
+  auto prefetchable = [&](int job) { return job < nJ3 && job >= nJB && (single || job >= nJB + nJA); };
+
+  // state rows of this CTA's first P1 tile of step 0 (later steps: gathered under the Adam phase)
+  bool xs_ready = false;
+  if (cta < nJ1) {
+    if (tid < 32) sidx[tid] = a.perm[cursor0 * (long long)B + (cta / NTL) * 32 + tid];
+    __syncthreads();
+    for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[e] = i < D ? a.state[(size_t)sidx[r] * D + i] : 0.f; }
+    xs_ready = true;
+  }
+  __syncthreads();
 
   for (int s = 0; s < a.n_steps; ++s) {
-    // =========================== P1: h2 = relu(relu(x W1^T + b1) W2^T + b2) ===========================
-    for (int job = cta; job < ((skip & 1) ? 0 : MT * NTL); job += (int)nctas) {
+    const bool trace = (flags & 256) && s == a.n_steps - 1;
+    TR(0);
+    // =========================== P1: h2 = relu(relu(x W1^T + b1) W2^T + b2), partial head outputs ========
+    for (int job = cta; job < nJ1; job += (int)nctas) {
       const int mt = job / NTL, nt = job - mt * NTL;
       const int m0 = mt * 32, n0 = nt * 32;
       __syncthreads();
-      if (tid < 32) {
-        const int r = a.perm[(cursor0 + s) * (long long)B + m0 + tid];
-        sidx[tid] = r;
-        if (nt == 0) a.cur_idx[m0 + tid] = r;
+      stage_kc(st, R1, a.W2, H, n0, 0, H);
+      st.commit();
+      if (!(job == cta && xs_ready)) {
+        if (tid < 32) sidx[tid] = a.perm[(cursor0 + s) * (long long)B + m0 + tid];
+        __syncthreads();
+        for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[e] = i < D ? a.state[(size_t)sidx[r] * D + i] : 0.f; }
+        __syncthreads();
       }
-      stage_kc(Bs, a.W2, H, n0, 0, H);
-      __syncthreads();
-      for (int e = tid; e < 32 * D; e += NT) {
-        const int r = e / D, i = e - r * D;
-        const float v = a.state[(size_t)sidx[r] * D + i];
-        xs[i * 32 + r] = v;                                   // transposed: [i][r]
-        if (nt == 0) a.xg[(size_t)(m0 + r) * D + i] = v;
+      if (nt == 0) {
+        if (tid < 32) a.cur_idx[m0 + tid] = sidx[tid];
+        for (int e = tid; e < 32 * D; e += NT) { const int r = e / D, i = e - r * D; a.xg[(size_t)(m0 + r) * D + i] = xs[r * MAXD + i]; }
       }
-      __syncthreads();
-      for (int k = tid; k < H; k += NT) {
-        float w[MAXD];
+      float whr[MAXO];
 #pragma unroll
-        for (int i = 0; i < MAXD; ++i) w[i] = i < D ? ldcg(a.W1 + (size_t)k * D + i) : 0.f;
-        const float bb = ldcg(a.b1 + k);
-        float hacc[32];
+      for (int o = 0; o < MAXO; ++o) whr[o] = o < nout ? ldcg(ht.w[o] + n0 + lane) : 0.f;
+      const float b2v = ldcg(a.b2 + n0 + lane);
+      {
+        // h1 panel: thread = 4 adjacent hidden units x 16 rows
+        const int k = (tid & 127) * 4, rh = tid >> 7;
+        if (k < H) {
+          float w[4][MAXD];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) hacc[r] = 0.f;
+          for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-        for (int i = 0; i < MAXD; ++i) {
-          if (i < D) {                                         // uniform branch: no wasted issue slots for D < 16
-            const float wi = w[i];
+            for (int i = 0; i < MAXD; ++i) w[kk][i] = i < D ? ldcg(a.W1 + (size_t)(k + kk) * D + i) : 0.f;
+          const float4 bb = ldcg4(a.b1 + k);
+#pragma unroll 4
+          for (int r = 0; r < 16; ++r) {
+            const int row = rh * 16 + r;
+            float xr[MAXD];
 #pragma unroll
-            for (int r4 = 0; r4 < 8; ++r4) {
-              const float4 xv = *reinterpret_cast<const float4*>(&xs[i * 32 + r4 * 4]);
-              hacc[r4 * 4 + 0] = fmaf(xv.x, wi, hacc[r4 * 4 + 0]); hacc[r4 * 4 + 1] = fmaf(xv.y, wi, hacc[r4 * 4 + 1]);
-              hacc[r4 * 4 + 2] = fmaf(xv.z, wi, hacc[r4 * 4 + 2]); hacc[r4 * 4 + 3] = fmaf(xv.w, wi, hacc[r4 * 4 + 3]);
+            for (int i4 = 0; i4 < MAXD / 4; ++i4) {
+              if (i4 * 4 < D) {
+                const float4 t = *reinterpret_cast<const float4*>(&xs[row * MAXD + i4 * 4]);
+                xr[i4 * 4] = t.x; xr[i4 * 4 + 1] = t.y; xr[i4 * 4 + 2] = t.z; xr[i4 * 4 + 3] = t.w;
+              } else { xr[i4 * 4] = xr[i4 * 4 + 1] = xr[i4 * 4 + 2] = xr[i4 * 4 + 3] = 0.f; }
             }
+            float h[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < MAXD; ++i) {
+              if (i < D) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) h[kk] = fmaf(xr[i], w[kk][i], h[kk]);
+              }
+            }
+            const float4 hv = make_float4(fmaxf(h[0] + bb.x, 0.f), fmaxf(h[1] + bb.y, 0.f), fmaxf(h[2] + bb.z, 0.f), fmaxf(h[3] + bb.w, 0.f));
+            *reinterpret_cast<float4*>(&R0[row * (H + 4) + k]) = hv;
+            if (nt == 0) *reinterpret_cast<float4*>(&a.h1[((size_t)(k >> 5) * B + m0 + row) * 32 + (k & 31)]) = hv;   // tiled [H/32][B][32]
           }
         }
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const float hv = fmaxf(hacc[r] + bb, 0.f);
-          As[r * (H + 4) + k] = hv;
-          if (nt == 0) a.h1[(size_t)(m0 + r) * H + k] = hv;
-        }
       }
-      cp_commit_wait();
+      TR(1);
+      st.wait();
       __syncthreads();
+      TR(2);
       float acc[8][8] = {};
-      tile_mma<true, true>(As, Bs, H, acc, nullptr);
+      tile_mma<true, true>(R0, R1, H, acc, nullptr);
+      __syncthreads();
+      TR(3);
       float outv[4];
-      tile_reduce<true, true>(acc, As, outv);
+      tile_reduce<true, true>(acc, R0, outv);
+      TR(4);
+      {
+        float hp_[4][MAXO];                                  // 4 rows x nout products, butterflies interleaved
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int e = tid + r * NT, m = e >> 5, n = e & 31;
-        const float v = outv[r] + ldcg(a.b2 + n0 + n);
-        a.h2[(size_t)(m0 + m) * H + n0 + n] = fmaxf(v, 0.f);
-      }
-    }
-    grid_bar(a.barrier, epoch, nctas);
-
-    // =========================== P2: heads + loss rows (warp per row) ==================================
-    for (int b = cta * (NT / 32) + warp; b < ((skip & 2) ? 0 : B); b += (int)nctas * (NT / 32)) {
-      const float* hrow = a.h2 + (size_t)b * H;
-      float hv[PK / 32];
+        for (int r = 0; r < 4; ++r) {
+          const float v = fmaxf(outv[r] + b2v, 0.f);
+          a.h2[(size_t)(m0 + warp + 8 * r) * H + n0 + lane] = v;   // e = tid + r*256 -> (m = e >> 5, n = lane)
+          a.h2t[((size_t)nt * B + m0 + warp + 8 * r) * 32 + lane] = v;   // and the tiled copy [H/32][B][32]
 #pragma unroll
-      for (int j = 0; j < PK / 32; ++j) { const int k = lane + 32 * j; hv[j] = k < H ? ldcg(hrow + k) : 0.f; }
-      float ov[MAXO];
-#pragma unroll
-      for (int o = 0; o < MAXO; ++o) {
-        float acc = 0.f;
-        if (o < nout) {
-          float wv[PK / 32];
-#pragma unroll
-          for (int j = 0; j < PK / 32; ++j) { const int k = lane + 32 * j; wv[j] = k < H ? ldcg(ht.w[o] + k) : 0.f; }
-#pragma unroll
-          for (int j = 0; j < PK / 32; ++j) acc = fmaf(hv[j], wv[j], acc);
-          acc = jb_warp_sum(acc) + ldcg(ht.b[o]);
+          for (int o = 0; o < MAXO; ++o) hp_[r][o] = v * whr[o];
         }
-        ov[o] = acc;
-      }
-      if (lane == 0) {
-        const int r = __ldcg(a.cur_idx + b);
-        jbppo::RowOut ro;
-        if (a.continuous)
-          jbppo::row<true>(ov, A, 0, (const float*)a.action + (size_t)r * A, a.adv[r], a.ret[r], a.vold[r],
-                           a.logp_old + (size_t)r * A, hp, invB, ro);
-        else
-          jbppo::row<false>(ov, A, ((const int32_t*)a.action)[r], nullptr, a.adv[r], a.ret[r], a.vold[r],
-                            a.logp_old + r, hp, invB, ro);
-        float* rb = a.rowbuf + (size_t)b * ROWBUF;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) rb[q] = ro.dpol[q];
-        rb[16] = ro.dv1; rb[17] = ro.dv2; rb[18] = ro.sq1; rb[19] = ro.sq2;
-        rb[20] = ro.surr_min; rb[21] = ro.ent; rb[22] = ro.ratio; rb[23] = ro.pmin;
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int o = 0; o < MAXO; ++o)
+              if (o < nout) hp_[r][o] += __shfl_xor_sync(0xffffffffu, hp_[r][o], off);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float mine = 0.f;
+#pragma unroll
+          for (int o = 0; o < MAXO; ++o) if (lane == o && o < nout) mine = hp_[r][o];
+          if (lane < 4 * nq) a.headp[(((size_t)nt * 2 + (lane >> 2)) * B + m0 + warp + 8 * r) * 4 + (lane & 3)] = mine;
+        }
       }
     }
+    xs_ready = false;
+    TR(5);
     grid_bar(a.barrier, epoch, nctas);
+    TR(6);
 
-    // =========================== P3: backward tiles ====================================================
-    // critic means (every CTA, fixed order) -> which branch of max(c1, c2) carries the gradient; then the
-    // resolved d loss / d head outputs of the whole minibatch into shared memory
+    // =========================== P3: row phase + backward jobs =========================================
+    int pre_job = -1;                              // job whose first panels are already in flight
+    if (cta < nJ3 && (cta < nJB || prefetchable(cta))) { issue_stage(cta); pre_job = cta; }
+    // row ids of the NEXT step's first P1 tile: the load is in flight during the whole phase
+    const bool has_next = (s + 1 < a.n_steps) && cta < nJ1;
+    int next_r = 0;
+    if (has_next && tid < 32) next_r = a.perm[(cursor0 + s + 1) * (long long)B + (cta / NTL) * 32 + tid];
+
     float c1, c2;
     {
-      float p1 = 0.f, p2 = 0.f;
-      for (int b = tid; b < B; b += NT) { p1 += ldcg(a.rowbuf + (size_t)b * ROWBUF + 18); p2 += ldcg(a.rowbuf + (size_t)b * ROWBUF + 19); }
-      const float t1 = block_sum0(p1, scr), t2 = block_sum0(p2, scr + 8);
-      if (tid == 0) { scr[16] = t1 * invB; scr[17] = t2 * invB; }
+      float p1 = 0.f, p2 = 0.f, ssum = 0.f, esum = 0.f, mr = -INFINITY, mp = INFINITY;
+#pragma unroll 1
+      for (int b = tid; b < B; b += NT) {
+        {
+          const int r = a.perm[(cursor0 + s) * (long long)B + b];
+          float ov[2 * jbppo::MAX_A + 1];                     // row() indexes up to 2*MAX_A statically
+#pragma unroll
+          for (int o = 0; o < 2 * jbppo::MAX_A + 1; ++o) ov[o] = 0.f;
+#pragma unroll
+          for (int o = 0; o < MAXO; ++o) if (o < nout) ov[o] = ldcg(ht.b[o]);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (q < nq) {                                    // 16 independent loads in flight, folded in tile order
+              float4 v[PK / 32];
+#pragma unroll
+              for (int nt = 0; nt < PK / 32; ++nt)
+                v[nt] = nt < NTL ? ldcg4(a.headp + (((size_t)nt * 2 + q) * B + b) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int nt = 0; nt < PK / 32; ++nt) {
+                if (nt < NTL) { ov[q * 4] += v[nt].x; ov[q * 4 + 1] += v[nt].y; ov[q * 4 + 2] += v[nt].z; ov[q * 4 + 3] += v[nt].w; }
+              }
+            }
+          }
+          jbppo::RowOut ro;
+          if (a.continuous)
+            jbppo::row<true>(ov, A, 0, (const float*)a.action + (size_t)r * A, a.adv[r], a.ret[r], a.vold[r],
+                             a.logp_old + (size_t)r * A, hp, invB, ro);
+          else
+            jbppo::row<false>(ov, A, ((const int32_t*)a.action)[r], nullptr, a.adv[r], a.ret[r], a.vold[r],
+                              a.logp_old + r, hp, invB, ro);
+#pragma unroll
+          for (int o = 0; o < MAXO; ++o) dsm[b * MAXO + o] = o < npol ? ro.dpol[o] : 0.f;
+          dsm[b * MAXO + npol] = ro.dv1; dvs[b] = ro.dv2;      // the two candidate value-head gradients, resolved below
+          p1 += ro.sq1; p2 += ro.sq2; ssum += ro.surr_min; esum += ro.ent;
+          mr = fmaxf(mr, ro.ratio); mp = fminf(mp, ro.pmin);
+        }
+      }
+      p1 = jb_warp_sum(p1); p2 = jb_warp_sum(p2); ssum = jb_warp_sum(ssum); esum = jb_warp_sum(esum);
+      mr = jb_warp_max(mr); mp = jb_warp_min(mp);
+      if (lane == 0) { float* q = scr + warp * 8; q[0] = p1; q[1] = p2; q[2] = ssum; q[3] = esum; q[4] = mr; q[5] = mp; }
       __syncthreads();
-      c1 = scr[16]; c2 = scr[17];
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) { t1 += scr[w * 8]; t2 += scr[w * 8 + 1]; }
+      c1 = t1 * invB; c2 = t2 * invB;
       float w1, w2;
       jbppo::critic_weights(c1, c2, w1, w2);
-      for (int e = tid; e < B * MAXO; e += NT) {
-        const int m = e >> 3, o = e & 7;
-        const float* rb = a.rowbuf + (size_t)m * ROWBUF;
-        float v = 0.f;
-        if (o < npol) v = ldcg(rb + o);
-        else if (o == npol) v = w1 * ldcg(rb + 16) + w2 * ldcg(rb + 17);
-        dsm[e] = v;
+      for (int b = tid; b < B; b += NT) dsm[b * MAXO + npol] = w1 * dsm[b * MAXO + npol] + w2 * dvs[b];
+      if (cta == (int)nctas - 1 && tid == 0) {
+        // learn()-level statistics of this minibatch (ppo.py:171-175), accumulated on the device
+        float s3 = 0.f, s4 = 0.f, xr = -INFINITY, xp = INFINITY;
+        for (int w = 0; w < NT / 32; ++w) { s3 += scr[w * 8 + 2]; s4 += scr[w * 8 + 3]; xr = fmaxf(xr, scr[w * 8 + 4]); xp = fminf(xp, scr[w * 8 + 5]); }
+        a.acc[0] += -s3 * invB;
+        a.acc[1] += fmaxf(c1, c2);
+        a.acc[2] += -s4 * invB / (a.continuous ? (float)A : 1.f);
+        a.acc[3] = fmaxf(a.acc[3], xr);
+        a.acc[4] = fminf(a.acc[4], xp);
+        a.acc[5] += 1.f;
       }
       __syncthreads();
     }
-    const int nJB = MT * NTL;          // dh1 tiles
-    const int nJA = NTL * NTL;         // dW2 tiles
-    const int nJC = NTL;               // head weight-gradient column jobs
-    for (int job = cta; job < ((skip & 4) ? 0 : nJB + nJA + nJC); job += (int)nctas) {
+    TR(7);
+
+    float sq = 0.f;                                // this thread's share of the step's squared gradient norm
+    for (int job = cta; job < nJ3; job += (int)nctas) {
       __syncthreads();
+      TR(8 + min(3, (job - cta) / (int)nctas));
+      const int next = job + (int)nctas;
       if (job < nJB) {
-        // ---- dh1 tile = ((dout Wh) * relu'(h2)) W2, masked by relu'(h1) -------------------------------
+        // ---- dh1 tile = ((dout Wh) * relu'(h2)) W2, masked by relu'(h1); partial dW1 / db1 ---------------
         const int mt = job / NTL, kt = job - mt * NTL;
         const int m0 = mt * 32, k0 = kt * 32;
-        stage_kc(As, a.h2, H, m0, 0, H);
-        stage_nonkc(Bs, a.W2, H, k0, 0, H);
-        float wr[2][MAXO];
+        if (pre_job != job) issue_stage(job);
+        const int c4 = (tid & 127) * 4, rh = tid >> 7;
+        float4 wr[MAXO];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int n = tid + u * NT;
+        for (int o = 0; o < MAXO; ++o) wr[o] = (o < nout && c4 < H) ? ldcg4(ht.w[o] + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[e] = i < D ? ldcg(a.xg + (size_t)(m0 + r) * D + i) : 0.f; }
+        float h1m[4];
 #pragma unroll
-          for (int o = 0; o < MAXO; ++o) wr[u][o] = (o < nout && n < H) ? ldcg(ht.w[o] + n) : 0.f;
-        }
-        cp_commit_wait();
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int n = tid + u * NT;
-          if (n < H) {
+        for (int r = 0; r < 4; ++r) h1m[r] = ldcg(a.h1 + ((size_t)kt * B + m0 + warp + 8 * r) * 32 + lane);
+        st.wait();
+        TR(12);
+        if (c4 < H) {
 #pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-              const float4 d0 = *reinterpret_cast<const float4*>(&dsm[(m0 + r) * MAXO]);
-              const float4 d1 = *reinterpret_cast<const float4*>(&dsm[(m0 + r) * MAXO + 4]);
-              float dot = d0.x * wr[u][0];
-              dot = fmaf(d0.y, wr[u][1], dot); dot = fmaf(d0.z, wr[u][2], dot); dot = fmaf(d0.w, wr[u][3], dot);
-              dot = fmaf(d1.x, wr[u][4], dot); dot = fmaf(d1.y, wr[u][5], dot); dot = fmaf(d1.z, wr[u][6], dot); dot = fmaf(d1.w, wr[u][7], dot);
-              const float hvv = As[r * (H + 4) + n];
-              As[r * (H + 4) + n] = hvv > 0.f ? dot : 0.f;
-            }
+          for (int r = 0; r < 16; ++r) {
+            const int row = rh * 16 + r;
+            float4* pa = reinterpret_cast<float4*>(&R0[row * (H + 4) + c4]);
+            *pa = dh2_quad(&dsm[(m0 + row) * MAXO], wr, *pa);
           }
         }
         __syncthreads();
+        TR(13);
         float acc[8][8] = {};
-        tile_mma<true, false>(As, Bs, H, acc, nullptr);
+        tile_mma<true, false>(R0, R1, H, acc, nullptr);
+        __syncthreads();
+        TR(14);
+        if (prefetchable(next)) { issue_stage(next); pre_job = next; }
         float outv[4];
-        tile_reduce<true, false>(acc, As, outv);
+        tile_reduce<true, false>(acc, R0, outv);
+        TR(15);
+        // partial dW1[k0+n][i] = sum_{m in tile} dh1[m, n] x[m, i], db1 likewise: 4 rows per thread, then 8 warps
+        float wacc[MAXD + 1];
+#pragma unroll
+        for (int i = 0; i <= MAXD; ++i) wacc[i] = 0.f;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const int e = tid + r * NT, m = e >> 5, n = e & 31;
-          const size_t off = (size_t)(m0 + m) * H + k0 + n;
-          a.dh1[off] = ldcg(a.h1 + off) > 0.f ? outv[r] : 0.f;
+          const float dv = h1m[r] > 0.f ? outv[r] : 0.f;
+          const float* xrow = &xs[(warp + 8 * r) * MAXD];
+#pragma unroll
+          for (int i = 0; i < MAXD; ++i) if (i < D) wacc[i] = fmaf(dv, xrow[i], wacc[i]);
+          wacc[MAXD] += dv;
         }
+#pragma unroll
+        for (int i = 0; i <= MAXD; ++i) if (i < D || i == MAXD) R0[(warp * (MAXD + 1) + i) * 32 + lane] = wacc[i];
+        __syncthreads();
+        for (int e = tid; e < 32 * (D + 1); e += NT) {
+          const int n = e / (D + 1), i = e - n * (D + 1);
+          const int slot = i < D ? i : MAXD;
+          float t = R0[(0 * (MAXD + 1) + slot) * 32 + n];
+#pragma unroll
+          for (int w = 1; w < NT / 32; ++w) t += R0[(w * (MAXD + 1) + slot) * 32 + n];
+          a.w1p[((size_t)mt * H + k0) * (D + 1) + e] = t;
+        }
+        __syncthreads();
+        if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(a.barrier + CTR_JB + kt) : "memory");
+        TR(16);
       } else if (job < nJB + nJA) {
-        // ---- dW2 tile [n0.., k0..] = sum_m dh2[m, n] h1[m, k]; db2 = row sums (k tile 0) ----------------
+        // ---- a pair of dW2 tiles [n0.., k0..] = sum_m dh2[m, n] h1[m, k] sharing the dh2 panel; db2 = its row sums
         const int j = job - nJB;
-        const int nt = j / NTL, kt = j - nt * NTL;
-        const int n0 = nt * 32, k0 = kt * 32;
-        float acc[8][8] = {};
-        float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const int c = tid & 31, ml = tid >> 5;
-        float wr[MAXO];
+        const int nt = j / NP, kt0 = 2 * (j - nt * NP);
+        const int n0 = nt * 32;
+        const int cg = tid & 7, rl = tid >> 3;
+        float4 wr[MAXO];
 #pragma unroll
-        for (int o = 0; o < MAXO; ++o) wr[o] = o < nout ? ldcg(ht.w[o] + n0 + c) : 0.f;
-        for (int mp = 0; mp < B; mp += PK) {
-          const int kp = min(PK, B - mp);
-          if (mp > 0) __syncthreads();
-          stage_nonkc(As, a.h2, H, n0, mp, kp);
-          stage_nonkc(Bs, a.h1, H, k0, mp, kp);
-          cp_commit_wait();
-          __syncthreads();
-#pragma unroll 4
-          for (int m = ml; m < kp; m += NT / 32) {
-            const float4 d0 = *reinterpret_cast<const float4*>(&dsm[(mp + m) * MAXO]);
-            const float4 d1 = *reinterpret_cast<const float4*>(&dsm[(mp + m) * MAXO + 4]);
-            float dot = d0.x * wr[0];
-            dot = fmaf(d0.y, wr[1], dot); dot = fmaf(d0.z, wr[2], dot); dot = fmaf(d0.w, wr[3], dot);
-            dot = fmaf(d1.x, wr[4], dot); dot = fmaf(d1.y, wr[5], dot); dot = fmaf(d1.z, wr[6], dot); dot = fmaf(d1.w, wr[7], dot);
-            const float hvv = As[m * 36 + c];
-            As[m * 36 + c] = hvv > 0.f ? dot : 0.f;
+        for (int o = 0; o < MAXO; ++o) wr[o] = o < nout ? ldcg4(ht.w[o] + n0 + 4 * cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int nhalf = (kt0 + 1 < NTL) ? 2 : 1;
+        for (int half = 0; half < nhalf; ++half) {
+          const int kt = kt0 + half, k0 = kt * 32;
+          const float* Bp = R1 + ((single && half == 1) ? R2_FLOATS : 0);
+          float acc[8][8] = {};
+          float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int mp = 0; mp < B; mp += JA_ROWS) {
+            const int kp = min(JA_ROWS, B - mp);
+            if (!single || half == 0) {
+              if (single) {
+                if (pre_job != job) issue_stage(job);
+              } else {
+                __syncthreads();
+                stage_block(st, R2, a.h2t + ((size_t)nt * B + mp) * 32, kp);
+                stage_block(st, R1, a.h1 + ((size_t)kt * B + mp) * 32, kp);
+                st.commit();
+              }
+              st.wait();
+              TR(17);
+              for (int m = rl; m < kp; m += 32) {
+                float4* pa = reinterpret_cast<float4*>(&R2[m * 32 + 4 * cg]);
+                *pa = dh2_quad(&dsm[(mp + m) * MAXO], wr, *pa);
+              }
+              __syncthreads();
+              TR(18);
+            }
+            tile_mma<false, false>(R2, Bp, kp, acc, kt == 0 ? rs : nullptr);
           }
           __syncthreads();
-          tile_mma<false, false>(As, Bs, kp, acc, kt == 0 ? rs : nullptr);
-        }
-        float outv[4];
-        tile_reduce<false, false>(acc, As, outv);
-        float sq = 0.f;
+          TR(19);
+          if (half == nhalf - 1 && prefetchable(next)) { issue_stage(next); pre_job = next; }
+          float outv[4];
+          tile_reduce<false, false>(acc, R0, outv);
+          TR(20);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int e = tid + r * NT, m = e >> 5, n = e & 31;
-          a.gW2[(size_t)(n0 + m) * H + k0 + n] = outv[r];
-          sq = fmaf(outv[r], outv[r], sq);
-        }
-        if (kt == 0) {
-          const int grp = tid >> 4, t = tid & 15, tx = t & 3, ty = t >> 2;
-          if (tx == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) As[grp * 32 + ty * 8 + i] = rs[i];
+          for (int r = 0; r < 4; ++r) {
+            a.gW2[(size_t)(n0 + warp + 8 * r) * H + k0 + lane] = outv[r];
+            sq = fmaf(outv[r], outv[r], sq);
           }
-          __syncthreads();
-          if (tid < 32) {
-            float v = 0.f;
+          if (kt == 0) {
+            const int grp = tid >> 4, t = tid & 15, tx = t & 3, ty = t >> 2;
+            if (tx == 0) {
 #pragma unroll
-            for (int g = 0; g < KG; ++g) v += As[g * 32 + tid];
-            a.gb2[n0 + tid] = v;
-            sq = fmaf(v, v, sq);
+              for (int i = 0; i < 8; ++i) R0[grp * 32 + ty * 8 + i] = rs[i];
+            }
+            __syncthreads();
+            if (tid < 32) {
+              float v = 0.f;
+#pragma unroll
+              for (int g = 0; g < KG; ++g) v += R0[g * 32 + tid];
+              a.gb2[n0 + tid] = v;
+              sq = fmaf(v, v, sq);
+            }
+            __syncthreads();
           }
         }
-        const float tot = block_sum0(sq, scr);
-        if (tid == 0) cta_norm += tot;
-      } else {
+        TR(21);
+      } else if (job < nJB + nJA + nJC) {
         // ---- head weight gradients, 32 columns per job; job 0 also the head bias gradients -------------
         const int jt = job - nJB - nJA;
-        const int j0 = jt * 32;
-        const int c = tid & 31, ml = tid >> 5;
+        const int j0 = jt * 32;   // first column of the tile
         float hacc[MAXO];
 #pragma unroll
         for (int o = 0; o < MAXO; ++o) hacc[o] = 0.f;
-        for (int mp = 0; mp < B; mp += PK) {
-          const int kp = min(PK, B - mp);
-          if (mp > 0) __syncthreads();
-          stage_nonkc(Bs, a.h2, H, j0, mp, kp);
-          cp_commit_wait();
-          __syncthreads();
+        for (int mp = 0; mp < B; mp += JA_ROWS) {
+          const int kp = min(JA_ROWS, B - mp);
+          if (!(mp == 0 && pre_job == job)) { __syncthreads(); stage_block(st, R2, a.h2t + ((size_t)jt * B + mp) * 32, kp); st.commit(); }
+          st.wait();
 #pragma unroll 4
-          for (int m = ml; m < kp; m += NT / 32) {
-            const float hvv = Bs[m * 36 + c];
+          for (int m = warp; m < kp; m += NT / 32) {
+            const float hvv = R2[m * 32 + lane];
             const float4 d0 = *reinterpret_cast<const float4*>(&dsm[(mp + m) * MAXO]);
             const float4 d1 = *reinterpret_cast<const float4*>(&dsm[(mp + m) * MAXO + 4]);
             hacc[0] = fmaf(d0.x, hvv, hacc[0]); hacc[1] = fmaf(d0.y, hvv, hacc[1]); hacc[2] = fmaf(d0.z, hvv, hacc[2]);
@@ -481,18 +671,19 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
             hacc[6] = fmaf(d1.z, hvv, hacc[6]); hacc[7] = fmaf(d1.w, hvv, hacc[7]);
           }
         }
-        float* red = As;               // [8][MAXO][32]
-#pragma unroll
-        for (int o = 0; o < MAXO; ++o) red[(ml * MAXO + o) * 32 + c] = hacc[o];
         __syncthreads();
-        float sq = 0.f;
-        if (ml == 0) {
+        if (prefetchable(next)) { issue_stage(next); pre_job = next; }
+        float* red = R0;               // [8][MAXO][32]
+#pragma unroll
+        for (int o = 0; o < MAXO; ++o) red[(warp * MAXO + o) * 32 + lane] = hacc[o];
+        __syncthreads();
+        if (warp == 0) {
 #pragma unroll
           for (int o = 0; o < MAXO; ++o) {
             if (o < nout) {
-              float t = red[(0 * MAXO + o) * 32 + c];
-              for (int r = 1; r < NT / 32; ++r) t += red[(r * MAXO + o) * 32 + c];
-              ht.gw[o][j0 + c] = t;
+              float t = red[(0 * MAXO + o) * 32 + lane];
+              for (int r = 1; r < NT / 32; ++r) t += red[(r * MAXO + o) * 32 + lane];
+              ht.gw[o][j0 + lane] = t;
               sq = fmaf(t, t, sq);
             }
           }
@@ -508,134 +699,121 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           if (tid < MAXO) {
             float tt = 0.f;
             for (int q = 0; q < NT / 8; ++q) tt += red[q * MAXO + tid];
-#pragma unroll
-            for (int u = 0; u < MAXO; ++u) if (u == tid && u < nout) { *ht.gb[u] = tt; sq = fmaf(tt, tt, sq); }
+            if (tid < nout) { *ht.gb[tid] = tt; sq = fmaf(tt, tt, sq); }
           }
         }
-        const float tot = block_sum0(sq, scr);
-        if (tid == 0) cta_norm += tot;
-      }
-    }
-    grid_bar(a.barrier, epoch, nctas);
-
-    // =========================== P4: dW1 / db1, statistics, norm partials ==============================
-    for (int job = cta; job < ((skip & 8) ? 0 : NTL); job += (int)nctas) {
-      __syncthreads();
-      const int j0 = job * 32, c = tid & 31, ml = tid >> 5;
-      float wacc[MAXD + 1];
-#pragma unroll
-      for (int i = 0; i <= MAXD; ++i) wacc[i] = 0.f;
-      for (int mp = 0; mp < B; mp += PK) {
-        const int kp = min(PK, B - mp);
-        if (mp > 0) __syncthreads();
-        stage_nonkc(As, a.dh1, H, j0, mp, kp);
-        for (int e = tid; e < kp * D; e += NT) { const int m = e / D, i = e - m * D; Bs[m * MAXD + i] = ldcg(a.xg + (size_t)mp * D + e); }
-        cp_commit_wait();
+      } else {
+        // ---- dW1 / db1 of 32 hidden units: fixed-order fold of the MT tile partials ----------------------
+        const int kt = job - nJB - nJA - nJC, k0 = kt * 32;
+        if (tid == 0) {
+          const unsigned int target = (unsigned int)MT * (unsigned int)(s + 1);
+          unsigned int v;
+          do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(a.barrier + CTR_JB + kt) : "memory");
+          } while (v < target);
+          asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+        }
         __syncthreads();
-        for (int m = ml; m < kp; m += NT / 32) {
-          const float dv = As[m * 36 + c];
-#pragma unroll
-          for (int i = 0; i < MAXD; ++i) if (i < D) wacc[i] = fmaf(dv, Bs[m * MAXD + i], wacc[i]);
-          wacc[MAXD] += dv;
+        for (int e = tid; e < 32 * (D + 1); e += NT) {
+          const int n = e / (D + 1), i = e - n * (D + 1);
+          float t = ldcg(a.w1p + (size_t)k0 * (D + 1) + e);
+          for (int mt = 1; mt < MT; ++mt) t += ldcg(a.w1p + ((size_t)mt * H + k0) * (D + 1) + e);
+          if (i < D) a.gW1[(size_t)(k0 + n) * D + i] = t; else a.gb1[k0 + n] = t;
+          sq = fmaf(t, t, sq);
         }
       }
-      float* red = dsm;                // [8][MAXD+1][32] = 4352 floats (dsm is dead after P3)
-#pragma unroll
-      for (int i = 0; i <= MAXD; ++i) red[(ml * (MAXD + 1) + i) * 32 + c] = wacc[i];
-      __syncthreads();
-      float sq = 0.f;
-      if (ml == 0) {
-#pragma unroll
-        for (int i = 0; i <= MAXD; ++i) {
-          if (i < D || i == MAXD) {
-            float t = red[(0 * (MAXD + 1) + i) * 32 + c];
-            for (int r = 1; r < NT / 32; ++r) t += red[(r * (MAXD + 1) + i) * 32 + c];
-            if (i < D) a.gW1[(size_t)(j0 + c) * D + i] = t; else a.gb1[j0 + c] = t;
-            sq = fmaf(t, t, sq);
-          }
-        }
-      }
-      const float tot = block_sum0(sq, scr);
-      if (tid == 0) cta_norm += tot;
     }
-    if (cta == (int)nctas - 1) {
-      // learn()-level statistics of this minibatch (ppo.py:171-175), accumulated on the device
-      float ssum = 0.f, esum = 0.f, mr = -INFINITY, mp = INFINITY;
-      for (int b = tid; b < B; b += NT) {
-        const float* rb = a.rowbuf + (size_t)b * ROWBUF;
-        ssum += ldcg(rb + 20); esum += ldcg(rb + 21);
-        mr = fmaxf(mr, ldcg(rb + 22)); mp = fminf(mp, ldcg(rb + 23));
-      }
-      const float t1 = block_sum0(ssum, scr), t2 = block_sum0(esum, scr + 8);
-      mr = jb_warp_max(mr); mp = jb_warp_min(mp);
-      __syncthreads();
-      if (lane == 0) { scr[32 + warp] = mr; scr[48 + warp] = mp; }
-      __syncthreads();
-      if (tid == 0) {
-        for (int w = 1; w < NT / 32; ++w) { mr = fmaxf(mr, scr[32 + w]); mp = fminf(mp, scr[48 + w]); }
-        a.acc[0] += -t1 * invB;
-        a.acc[1] += fmaxf(c1, c2);
-        a.acc[2] += -t2 * invB / (a.continuous ? (float)A : 1.f);
-        a.acc[3] = fmaxf(a.acc[3], mr);
-        a.acc[4] = fminf(a.acc[4], mp);
-        a.acc[5] += 1.f;
-      }
+    TR(22);
+    {
+      const float tot = block_sum(sq, scr + 64);
+      if (tid == 0) a.partials[cta] = tot;
     }
-    if (tid == 0) { a.partials[cta] = cta_norm; cta_norm = 0.f; }
+    if (has_next && tid < 32) sidx[tid] = next_r;
+    // Adam operands that do not depend on this step's gradient: in registers across the barrier
+    float4 pp[ADAM_IT], mm[ADAM_IT], vv[ADAM_IT];
+#pragma unroll
+    for (int it = 0; it < ADAM_IT; ++it) {
+      const long long i = lo + tid + it * NT;
+      if (i < hi) { pp[it] = __ldcg(p4 + i); mm[it] = __ldcg(m4 + i); vv[it] = __ldcg(v4 + i); }
+    }
+    TR(23);
     grid_bar(a.barrier, epoch, nctas);
+    TR(24);
 
     // =========================== P5: clip + Adam on this CTA's slice ===================================
-    if (!(skip & 16)) {
+    {
+      float4 gg[ADAM_IT];
+#pragma unroll
+      for (int it = 0; it < ADAM_IT; ++it) {
+        const long long i = lo + tid + it * NT;
+        if (i < hi) gg[it] = __ldcg(g4 + i);
+      }
+      // next step's state rows (sidx was published before the barrier)
+      float xv[2] = {0.f, 0.f};
+      if (has_next) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { const int e = tid + q * NT, r = e >> 4, i = e & 15; if (i < D) xv[q] = a.state[(size_t)sidx[r] * D + i]; }
+      }
+      // ||g||: every warp folds all partials in the same fixed order (no shared memory, no CTA barrier)
+      float pv[NT / 32];
+#pragma unroll
+      for (int q = 0; q < NT / 32; ++q) pv[q] = lane + 32 * q < (int)nctas ? ldcg(a.partials + lane + 32 * q) : 0.f;
       double t = 0.0;
-      for (int k = tid; k < (int)nctas; k += NT) t += (double)ldcg(a.partials + k);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      double* dscr = reinterpret_cast<double*>(scr + 64);
-      __syncthreads();
-      if (lane == 0) dscr[warp] = t;
-      __syncthreads();
-      double tot = 0.0;
-#pragma unroll
-      for (int w = 0; w < NT / 32; ++w) tot += dscr[w];
-      const float total_norm = (float)sqrt(tot);
+      for (int q = 0; q < NT / 32; ++q) t += (double)pv[q];
+      t = jb_warp_sum_d(t);
+      const float total_norm = (float)sqrt(t);
       float coef = 1.f;
       if (a.max_norm > 0.f) { coef = a.max_norm / (total_norm + 1e-6f); coef = coef < 1.f ? coef : 1.f; }
-      if (tid == 0) {                                  // bias corrections once per CTA (double pow is ~200 instructions)
-        const double tt = (double)(step0 + s + 1);
-        const double bc1 = 1.0 - pow((double)a.beta1, tt), bc2 = 1.0 - pow((double)a.beta2, tt);
-        scr[96] = (float)((double)lr / bc1);
-        scr[97] = (float)sqrt(bc2);
-      }
-      __syncthreads();
-      const float step_size = scr[96], bc2_sqrt = scr[97];
-      const float one_m_b1 = 1.f - a.beta1, one_m_b2 = 1.f - a.beta2;
-      auto upd = [&](float& pp, float gg, float& mm, float& vv) {
-        gg *= coef;
-        mm = fmaf(gg - mm, one_m_b1, mm);
-        vv = fmaf(one_m_b2 * gg, gg, a.beta2 * vv);
-        const float denom = sqrtf(vv) / bc2_sqrt + a.adam_eps;
-        pp = fmaf(-step_size, mm / denom, pp);
+      const float step_size = (float)((double)lr / (1.0 - pw1));
+      const float bc2_sqrt = (float)sqrt(1.0 - pw2);
+      pw1 *= (double)a.beta1; pw2 *= (double)a.beta2;
+      TR(25);
+      // sqrt / reciprocal by the MUFU approximations (<= 2 ulp): the quotient only scales a term that is
+      // ~lr times smaller than the parameter it is added to, so the rounding of p is unchanged to ~1e-11
+      const float inv_bc2 = 1.f / bc2_sqrt;
+      auto upd = [&](float& p_, float g_, float& m_, float& v_) {
+        g_ *= coef;
+        m_ = fmaf(g_ - m_, one_m_b1, m_);
+        v_ = fmaf(one_m_b2 * g_, g_, a.beta2 * v_);
+        float sq_, rc_;
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(sq_) : "f"(v_));
+        const float denom = fmaf(sq_, inv_bc2, a.adam_eps);
+        asm("rcp.approx.f32 %0, %1;" : "=f"(rc_) : "f"(denom));
+        p_ = fmaf(-step_size, m_ * rc_, p_);
       };
-      const long long per = (a.P4 + nctas - 1) / nctas;
-      const long long lo = (long long)cta * per, hi = min(a.P4, lo + per);
-      float4* p4 = reinterpret_cast<float4*>(a.flat);
-      const float4* g4 = reinterpret_cast<const float4*>(a.grad);
-      float4* m4 = reinterpret_cast<float4*>(a.am);
-      float4* v4 = reinterpret_cast<float4*>(a.av);
-      for (long long i = lo + tid; i < hi; i += NT) {
-        float4 pp = __ldcg(p4 + i), mm = __ldcg(m4 + i), vv = __ldcg(v4 + i);
-        const float4 gg = __ldcg(g4 + i);
-        upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
-        p4[i] = pp; m4[i] = mm; v4[i] = vv;
+#pragma unroll
+      for (int it = 0; it < ADAM_IT; ++it) {
+        const long long i = lo + tid + it * NT;
+        if (i < hi) {
+          upd(pp[it].x, gg[it].x, mm[it].x, vv[it].x); upd(pp[it].y, gg[it].y, mm[it].y, vv[it].y);
+          upd(pp[it].z, gg[it].z, mm[it].z, vv[it].z); upd(pp[it].w, gg[it].w, mm[it].w, vv[it].w);
+          p4[i] = pp[it]; m4[i] = mm[it]; v4[i] = vv[it];
+          shadow(i, pp[it]);
+        }
+      }
+      for (long long i = lo + tid + (long long)ADAM_IT * NT; i < hi; i += NT) {   // slices beyond 8 K floats per CTA
+        float4 p_ = __ldcg(p4 + i), m_ = __ldcg(m4 + i), v_ = __ldcg(v4 + i);
+        const float4 g_ = __ldcg(g4 + i);
+        upd(p_.x, g_.x, m_.x, v_.x); upd(p_.y, g_.y, m_.y, v_.y); upd(p_.z, g_.z, m_.z, v_.z); upd(p_.w, g_.w, m_.w, v_.w);
+        p4[i] = p_; m4[i] = m_; v4[i] = v_;
+        shadow(i, p_);
+      }
+      if (has_next) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) xs[tid + q * NT] = xv[q];
+        xs_ready = true;
       }
     }
+    TR(26);
     grid_bar(a.barrier, epoch, nctas);
+    TR(27);
   }
   if (cta == 0 && tid == 0) { *a.step = step0 + a.n_steps; *a.cursor = cursor0 + a.n_steps; }
 }
 
-static int dsm_floats_for(int B) { const int need = B * MAXO; return need > 4352 ? need : 4352; }
-static size_t fused_smem(int B) { return sizeof(float) * (size_t)(SMALL_FLOATS + dsm_floats_for(B) + 2 * PANEL_FLOATS); }
+static int dsm_floats_for(int B) { return B * MAXO; }
+static size_t fused_smem(int B) { return sizeof(float) * (size_t)(SMALL_FLOATS + dsm_floats_for(B) + 2 * RED_FLOATS + R2_FLOATS); }
 
 // Largest grid the cooperative launch can keep co-resident (one CTA per SM on B200) for minibatch size B.
 static int fused_max_ctas(int B) {
@@ -655,24 +833,29 @@ JB_API int jb_ppo_fused_args_size(void) { return (int)sizeof(jb_ppo_fused_args);
 
 JB_API int jb_ppo_fused_max_ctas(void) { return fused_max_ctas(256); }
 
+// Debug: copy the clock64 trace of the last step (JB_FUSED_SKIP=256) to host memory: [256 CTAs][32 slots].
+JB_API int jb_ppo_fused_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 256 * 32) == cudaSuccess ? JB_OK : JB_ERR_CUDA;
+}
+
 // Runs args->n_steps minibatch steps starting at the device-side cursor.  `args` is a HOST pointer to
 // a jb_ppo_fused_args (include/jorldy_b200_fused.h); it is copied at launch.
 JB_API int jb_ppo_fused_run(const void* host_args, void* stream) {
   if (!host_args) return JB_ERR_INVALID;
   Args a = *reinterpret_cast<const Args*>(host_args);
-  if (a.B <= 0 || a.B % 32 || a.H <= 0 || a.H % 32 || a.H > PK || a.D <= 0 || a.D > MAXD || a.nout <= 0 || a.nout > MAXO ||
-      a.A <= 0 || a.A > jbppo::MAX_A || a.n_steps <= 0 || a.P4 <= 0)
+  if (a.B <= 0 || a.B % 32 || a.B > MAX_B || a.H <= 0 || a.H % 32 || a.H > PK || a.D <= 0 || a.D > MAXD || a.nout <= 0 ||
+      a.nout > MAXO || a.A <= 0 || a.A > jbppo::MAX_A || a.n_steps <= 0 || a.P4 <= 0)
     return JB_ERR_INVALID;
   int ctas = fused_max_ctas(a.B);
   if (ctas <= 0) return JB_ERR_INVALID;
   if (ctas > NT) ctas = NT;
   cudaStream_t s = (cudaStream_t)stream;
-  if (cudaMemsetAsync(a.barrier, 0, sizeof(unsigned int), s) != cudaSuccess) return JB_ERR_CUDA;
+  if (cudaMemsetAsync(a.barrier, 0, 64 * sizeof(unsigned int), s) != cudaSuccess) return JB_ERR_CUDA;   // grid counter + JB counters
   const size_t smem = fused_smem(a.B);
   int dsm_floats = dsm_floats_for(a.B);
-  int skip = 0;
-  if (const char* e = getenv("JB_FUSED_SKIP")) skip = atoi(e);     // timing experiments only
-  void* kargs[] = {&a, &dsm_floats, &skip};
+  int flags = 0;
+  if (const char* e = getenv("JB_FUSED_SKIP")) flags = atoi(e);     // bit 8: record the timing trace
+  void* kargs[] = {&a, &dsm_floats, &flags};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)ppo_epoch_kernel, dim3(ctas), dim3(NT), kargs, smem, s);
   if (e != cudaSuccess) { cudaGetLastError(); return JB_ERR_CUDA; }
   return JB_OK;

@@ -22,13 +22,19 @@ struct RowOut {
   float ratio, pmin;       // ratio; exp(log_prob) (continuous: min over dims)
 };
 
-__device__ __forceinline__ void log_softmax_row(const float* lg, int A, float* lsm) {
+// All per-action loops run over the compile-time bound MAX_A with an `a < A` guard: arrays stay in
+// registers (a run-time trip count would index them dynamically and put them in local memory) and the
+// arithmetic order is the plain ascending-a order of the restated definitions.
+__device__ __forceinline__ void log_softmax_row(const float (&lg)[MAX_A], int A, float (&lsm)[MAX_A]) {
   float mx = lg[0];
-  for (int a = 1; a < A; ++a) mx = fmaxf(mx, lg[a]);
+#pragma unroll
+  for (int a = 1; a < MAX_A; ++a) if (a < A) mx = fmaxf(mx, lg[a]);
   float s = 0.f;
-  for (int a = 0; a < A; ++a) s += expf(lg[a] - mx);
+#pragma unroll
+  for (int a = 0; a < MAX_A; ++a) if (a < A) s += expf(lg[a] - mx);
   const float ls = logf(s);
-  for (int a = 0; a < A; ++a) lsm[a] = (lg[a] - mx) - ls;
+#pragma unroll
+  for (int a = 0; a < MAX_A; ++a) lsm[a] = a < A ? (lg[a] - mx) - ls : 0.f;
 }
 
 __device__ __forceinline__ float atanh_clamped(float a) {
@@ -47,11 +53,14 @@ __device__ __forceinline__ void surrogate(float ratio, float adv, float eps, flo
   else g = 0.5f * adv + 0.5f * adv * inr;        // torch.minimum splits ties
 }
 
-// o: the row's head outputs [nout]; a_disc / a_cont: the stored action; lpo: log_prob_old (1 or A values)
+// o: the row's head outputs [nout] (at least 2*MAX_A... entries readable up to index nout-1); a_disc / a_cont:
+// the stored action; lpo: log_prob_old (1 or A values)
 template <bool CONT>
 __device__ __forceinline__ void row(const float* o, int A, int a_disc, const float* a_cont, float adv, float ret,
                                     float vold, const float* lpo, HP hp, float invB, RowOut& r) {
-  const float v = o[CONT ? 2 * A : A];
+  float v = 0.f;                                   // o[CONT ? 2A : A] without a run-time register index
+#pragma unroll
+  for (int q = 0; q < 2 * MAX_A + 1; ++q) if (q == (CONT ? 2 * A : A)) v = o[q];
   const float dv_raw = v - vold;
   const float vclip = vold + fminf(fmaxf(dv_raw, -hp.eps_clip), hp.eps_clip);
   const float in_clip = (dv_raw >= -hp.eps_clip && dv_raw <= hp.eps_clip) ? 1.f : 0.f;
@@ -59,21 +68,29 @@ __device__ __forceinline__ void row(const float* o, int A, int a_disc, const flo
   r.sq1 = d1 * d1; r.sq2 = d2 * d2;
   r.dv1 = hp.vf_coef * invB * 2.f * d1;
   r.dv2 = hp.vf_coef * invB * 2.f * d2 * in_clip;
+#pragma unroll
+  for (int q = 0; q < 2 * MAX_A; ++q) r.dpol[q] = 0.f;
   if (!CONT) {
     float lg[MAX_A], lsm[MAX_A], pi[MAX_A], p[MAX_A], lc[MAX_A], inr[MAX_A];
-    for (int a = 0; a < A; ++a) lg[a] = o[a];
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) lg[a] = a < A ? o[a] : 0.f;
     log_softmax_row(lg, A, lsm);
     float S = 0.f;
-    for (int a = 0; a < A; ++a) { pi[a] = expf(lsm[a]); S += pi[a]; }
-    float ent = 0.f;
-    for (int a = 0; a < A; ++a) {
-      p[a] = pi[a] / S;
-      const float pc = fminf(fmaxf(p[a], F32_EPS), 1.f - F32_EPS);
-      inr[a] = (p[a] >= F32_EPS && p[a] <= 1.f - F32_EPS) ? 1.f : 0.f;
-      lc[a] = logf(pc);
-      ent -= lc[a] * p[a];
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) { pi[a] = 0.f; if (a < A) { pi[a] = expf(lsm[a]); S += pi[a]; } }
+    float ent = 0.f, logp = 0.f;
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) {
+      p[a] = 1.f; lc[a] = 0.f; inr[a] = 0.f;
+      if (a < A) {
+        p[a] = pi[a] / S;
+        const float pc = fminf(fmaxf(p[a], F32_EPS), 1.f - F32_EPS);
+        inr[a] = (p[a] >= F32_EPS && p[a] <= 1.f - F32_EPS) ? 1.f : 0.f;
+        lc[a] = logf(pc);
+        ent -= lc[a] * p[a];
+        if (a == a_disc) logp = lc[a];
+      }
     }
-    const float logp = lc[a_disc];
     const float ratio = expf(logp - lpo[0]);
     float smin, gr;
     surrogate(ratio, adv, hp.eps_clip, smin, gr);
@@ -81,34 +98,55 @@ __device__ __forceinline__ void row(const float* o, int A, int a_disc, const flo
     const float dlogp = -gr * ratio * invB;            // d(actor_loss)/d log_prob
     const float dent = -hp.ent_coef * invB;            // d(ent_coef * entropy_loss)/d entropy_b
     float dp[MAX_A], dot = 0.f;
-    for (int a = 0; a < A; ++a) {
-      float t = dent * (-(lc[a] + inr[a]));
-      if (a == a_disc) t += dlogp * inr[a] / p[a];
-      dp[a] = t;
-      dot += t * pi[a];
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) {
+      dp[a] = 0.f;
+      if (a < A) {
+        float t = dent * (-(lc[a] + inr[a]));
+        if (a == a_disc) t += dlogp * inr[a] / p[a];
+        dp[a] = t;
+        dot += t * pi[a];
+      }
     }
     float dlsm[MAX_A], sum_dlsm = 0.f;
-    for (int a = 0; a < A; ++a) {
-      const float dpi = dp[a] / S - dot / (S * S);
-      dlsm[a] = dpi * pi[a];
-      sum_dlsm += dlsm[a];
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) {
+      dlsm[a] = 0.f;
+      if (a < A) {
+        const float dpi = dp[a] / S - dot / (S * S);
+        dlsm[a] = dpi * pi[a];
+        sum_dlsm += dlsm[a];
+      }
     }
-    for (int a = 0; a < A; ++a) r.dpol[a] = dlsm[a] - expf(lsm[a]) * sum_dlsm;
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) if (a < A) r.dpol[a] = dlsm[a] - expf(lsm[a]) * sum_dlsm;
   } else {
     const float log_sqrt_2pi = 0.9189385332046727f;
     float dsum = 0.f, ent = 0.f;
-    float mu[MAX_A], sd[MAX_A], ls[MAX_A], z[MAX_A];
+    float omu[MAX_A], ols[MAX_A], mu[MAX_A], sd[MAX_A], ls[MAX_A], z[MAX_A], dmu_[MAX_A], dls_[MAX_A];
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) {                 // o[a] and o[A + a] without run-time register indices
+      omu[a] = a < A ? o[a] : 0.f;
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 2 * MAX_A; ++q) if (q == A + a && a < A) t = o[q];
+      ols[a] = t;
+    }
     float pmin = INFINITY;
-    for (int a = 0; a < A; ++a) {
-      mu[a] = fminf(fmaxf(o[a], -5.f), 5.f);
-      ls[a] = tanhf(o[A + a]);
-      sd[a] = expf(ls[a]);
-      z[a] = atanh_clamped(a_cont[a]);
-      const float d = z[a] - mu[a];
-      const float logp = -(d * d) / (2.f * (sd[a] * sd[a])) - logf(sd[a]) - log_sqrt_2pi;
-      dsum += logp - lpo[a];
-      ent += 0.5f + 0.5f * 1.8378770664093453f + logf(sd[a]);
-      pmin = fminf(pmin, expf(logp));
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) {
+      mu[a] = sd[a] = ls[a] = z[a] = 0.f;
+      if (a < A) {
+        mu[a] = fminf(fmaxf(omu[a], -5.f), 5.f);
+        ls[a] = tanhf(ols[a]);
+        sd[a] = expf(ls[a]);
+        z[a] = atanh_clamped(a_cont[a]);
+        const float d = z[a] - mu[a];
+        const float logp = -(d * d) / (2.f * (sd[a] * sd[a])) - logf(sd[a]) - log_sqrt_2pi;
+        dsum += logp - lpo[a];
+        ent += 0.5f + 0.5f * 1.8378770664093453f + logf(sd[a]);
+        pmin = fminf(pmin, expf(logp));
+      }
     }
     const float ratio = expf(dsum);
     float smin, gr;
@@ -116,14 +154,28 @@ __device__ __forceinline__ void row(const float* o, int A, int a_disc, const flo
     r.surr_min = smin; r.ent = ent; r.ratio = ratio; r.pmin = pmin;
     const float dlogp = -gr * ratio * invB;
     const float dent = -hp.ent_coef * invB / (float)A;   // entropy_loss = -mean over B*A elements
-    for (int a = 0; a < A; ++a) {
-      const float d = z[a] - mu[a];
-      const float var = sd[a] * sd[a];
-      const float dmu = dlogp * d / var;
-      const float dsd = dlogp * (d * d / (var * sd[a]) - 1.f / sd[a]) + dent / sd[a];
-      const float in_mu = (o[a] >= -5.f && o[a] <= 5.f) ? 1.f : 0.f;
-      r.dpol[a] = dmu * in_mu;
-      r.dpol[A + a] = dsd * sd[a] * (1.f - ls[a] * ls[a]);
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) {
+      dmu_[a] = dls_[a] = 0.f;
+      if (a < A) {
+        const float d = z[a] - mu[a];
+        const float var = sd[a] * sd[a];
+        const float dmu = dlogp * d / var;
+        const float dsd = dlogp * (d * d / (var * sd[a]) - 1.f / sd[a]) + dent / sd[a];
+        const float in_mu = (omu[a] >= -5.f && omu[a] <= 5.f) ? 1.f : 0.f;
+        dmu_[a] = dmu * in_mu;
+        dls_[a] = dsd * sd[a] * (1.f - ls[a] * ls[a]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2 * MAX_A; ++q) {
+      float t = 0.f;
+#pragma unroll
+      for (int a = 0; a < MAX_A; ++a) {
+        if (a < A && q == a) t = dmu_[a];
+        if (a < A && q == A + a) t = dls_[a];
+      }
+      r.dpol[q] = t;
     }
   }
 }
