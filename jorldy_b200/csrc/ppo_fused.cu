@@ -47,11 +47,12 @@ constexpr int MAXD = 16;
 constexpr int MAXO = 8;
 constexpr int KG = 16;                                  // in-CTA split-K groups
 constexpr int SMALL_FLOATS = 2048;                      // xs[32*16], reduction scratch, row ids
-constexpr int RED_FLOATS = KG * (32 * 36 + 16);         // 18688: split-K fold area; also >= a 32x(PK+4) or PKx36 panel
+constexpr int RED_FLOATS = KG * (32 * 36 + 16);   /* = KG * RED_GS */         // 18688: split-K fold area; also >= a 32x(PK+4) or PKx36 panel
 constexpr int JA_ROWS = 256;                            // minibatch rows per dW2 / head-gradient panel
 constexpr int R2_FLOATS = JA_ROWS * 32;                 // 8192: a dense [256][32] panel
 constexpr int MAX_B = 512;                              // minibatch rows (row-phase scratch in s_small)
 constexpr int ADAM_IT = 8;                              // float4 per thread kept in registers across the barrier
+constexpr int PS_FLOATS = (MAXO + 2) * PK;                // per-CTA parameter stash: head rows [MAXO][PK], b2, b1
 constexpr int CTR_JB = 32;                              // a.barrier[CTR_JB + kt]: finished JB jobs of column tile kt
 
 typedef jb_ppo_fused_args Args;
@@ -193,29 +194,28 @@ template <bool A_KC>
 __device__ __forceinline__ int tile_row(int ty, int i) { return A_KC ? (ty + 4 * i) : (ty * 8 + i); }
 
 // fold the 16 k-groups in a fixed order; thread gets outputs e = tid + r*256 -> (m = e>>5, n = e&31).
-// Layout of `red` (RED_FLOATS): row stride 36, odd groups shifted by 16 banks, columns rotated by 4*(m>>3)
-// for [k][32] A panels: the 64 partial-tile stores of a warp are conflict-free (k-contiguous panels) or
-// at most 2-way.  The caller has synchronised the CTA since the last read of the memory behind `red`.
-template <bool A_KC>
-__device__ __forceinline__ int red_index(int grp, int m, int n) {
-  const int rot = A_KC ? 0 : 4 * (m >> 3);
-  return grp * (32 * 36 + 16) + m * 36 + ((n + rot) & 31) + (grp & 1) * 16;   // group stride keeps the shifted rows apart
-}
+// The caller has synchronised the CTA since the last read of the memory behind `red` (RED_FLOATS).
+// Element (i, j) of thread (ty, tx) always goes to slot (ty + 4 i, tx + 4 j) of its group's 32 x 36 block,
+// whatever tile row / column it stands for: the 32 lanes of a store then hit 32 distinct banks (group blocks
+// are 16 banks apart).  The reader maps its output (m, n) back through the panel's row order.
+constexpr int RED_GS = 32 * 36 + 16;
+template <bool KC>
+__device__ __forceinline__ int red_slot(int idx) { return KC ? idx : ((idx >> 3) + 4 * (idx & 7)); }
 template <bool A_KC, bool B_KC>
 __device__ __forceinline__ void tile_reduce(const float (&acc)[8][8], float* red, float (&outv)[4]) {
   const int tid = threadIdx.x, grp = tid >> 4, t = tid & 15, tx = t & 3, ty = t >> 2;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      red[red_index<A_KC>(grp, tile_row<A_KC>(ty, i), tile_row<B_KC>(tx, j))] = acc[i][j];
+    for (int j = 0; j < 8; ++j) red[grp * RED_GS + (ty + 4 * i) * 36 + tx + 4 * j] = acc[i][j];
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int e = tid + r * NT, m = e >> 5, n = e & 31;
+    const int off = red_slot<A_KC>(m) * 36 + red_slot<B_KC>(n);
     float v = 0.f;
 #pragma unroll
-    for (int g = 0; g < KG; ++g) v += red[red_index<A_KC>(g, m, n)];
+    for (int g = 0; g < KG; ++g) v += red[g * RED_GS + off];
     outv[r] = v;
   }
   __syncthreads();
@@ -247,8 +247,8 @@ __device__ __forceinline__ float4 dh2_quad(const float* drow, const float4 (&wr)
 }
 
 // timing trace (debug; JB_FUSED_SKIP bit 8): clock64 at fixed points of the LAST step, per CTA, 32 slots
-__device__ long long g_trace[256 * 32];
-#define TR(i) do { if (trace && tid == 0) g_trace[cta * 32 + (i)] = clock64(); } while (0)
+__device__ long long g_trace[256 * 48];
+#define TR(i) do { if (trace && tid == 0) g_trace[cta * 48 + (i)] = clock64(); } while (0)
 
 struct HeadTab { const float* w[MAXO]; const float* b[MAXO]; float* gw[MAXO]; float* gb[MAXO]; };
 
@@ -258,13 +258,17 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   float* dsm = smem + SMALL_FLOATS;            // d loss/d head-outputs of the whole minibatch [B][MAXO]
   float* R0 = dsm + dsm_floats;                // RED_FLOATS: A panels of P1 / JB, split-K fold area, job scratch
   float* R1 = R0 + RED_FLOATS;                 // RED_FLOATS: B panels
-  float* R2 = R1 + RED_FLOATS;                 // R2_FLOATS:  A panel of JA / JC
+  float* R2 = R1 + RED_FLOATS;                 // R2_FLOATS:  A panel of JA / JC; W1 during P1
+  float* PS = R2 + R2_FLOATS;                  // PS_FLOATS:  head weight rows, b2, b1 of the current step
   float* xs = s_small;                         // [32][MAXD] state rows of the current tile (zero padded)
   float* scr = s_small + 768;                  // reduction scratch [128]
   int* sidx = reinterpret_cast<int*>(s_small + 1024);   // [32] gathered rollout row ids of the P1 tile
   Stager st;
-  st.init(s_small + 1056);                     // 8-byte mbarrier
-  float* dvs = s_small + 1088;                 // [MAX_B] second candidate value-head gradient of every row
+  st.init(s_small + 1056);                     // 8-byte mbarrier: panels
+  Stager stp;
+  stp.init(s_small + 1058);                    // 8-byte mbarrier: parameter stash
+  float* dvs = s_small + 1088;                 // [MAX_B] second candidate value-head gradient of every row (P3); norm partials (P5)
+  float* hb = s_small + 1600;                  // [MAXO] head biases
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned int nctas = gridDim.x;
@@ -336,6 +340,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   // may the panels of `job` be fetched while the previous job still folds in R0?
   auto prefetchable = [&](int job) { return job < nJ3 && job >= nJB && (single || job >= nJB + nJA); };
 
+  // rollout rows of this thread's minibatch rows (row phase), one step ahead
+  int pr[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) pr[q] = tid + q * NT < B ? a.perm[cursor0 * (long long)B + tid + q * NT] : 0;
   // state rows of this CTA's first P1 tile of step 0 (later steps: gathered under the Adam phase)
   bool xs_ready = false;
   if (cta < nJ1) {
@@ -349,13 +357,51 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   for (int s = 0; s < a.n_steps; ++s) {
     const bool trace = (flags & 256) && s == a.n_steps - 1;
     TR(0);
+    __syncthreads();                               // (step 0: the prologue; later steps: a no-op after the barrier)
     // =========================== P1: h2 = relu(relu(x W1^T + b1) W2^T + b2), partial head outputs ========
+    // rollout values of this thread's rows: issued first, parked in dsm (dead until the row phase) below
+    float pg[2][5];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (tid + q * NT < B) {
+        const int r = pr[q];
+        pg[q][0] = a.adv[r]; pg[q][1] = a.ret[r]; pg[q][2] = a.vold[r];
+        if (!a.continuous) { pg[q][3] = a.logp_old[r]; pg[q][4] = __int_as_float(((const int32_t*)a.action)[r]); }
+      }
+    }
+    if (cta < nJ1) { stage_kc(st, R1, a.W2, H, (cta % NTL) * 32, 0, H); st.commit(); }
+    // parameter stash: ONE bulk request per tensor per CTA.  (Per-thread loads of W1 / b1 / b2 / head rows had
+    // every warp of every CTA hit the same few KB right after the barrier: > 500 K sector requests queued on
+    // ~100 L2 lines, 4-5 us before the first value arrived.)
+    if (tid == 0) {
+      stp.copy(R2, a.W1, (unsigned)(H * D) * 4u);
+      stp.copy(PS + (MAXO + 1) * PK, a.b1, (unsigned)H * 4u);
+      stp.copy(PS + MAXO * PK, a.b2, (unsigned)H * 4u);
+      for (int o = 0; o < nout; ++o) stp.copy(PS + o * PK, ht.w[o], (unsigned)H * 4u);
+    }
+    if (tid >= 32 && tid < 32 + nout) hb[tid - 32] = ldcg(ht.b[tid - 32]);   // not warp 0: it must reach the arrive below
+    stp.bytes = (unsigned)(H * D + (2 + nout) * H) * 4u;
+    stp.commit();
+    TR(28);
+    stp.wait();
+    TR(29);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int b = tid + q * NT;
+      if (b < B) {
+        float* d = dsm + b * MAXO;
+        d[0] = pg[q][0]; d[1] = pg[q][1]; d[2] = pg[q][2]; d[5] = __int_as_float(pr[q]);
+        if (!a.continuous) { d[3] = pg[q][3]; d[4] = pg[q][4]; }
+      }
+    }
     for (int job = cta; job < nJ1; job += (int)nctas) {
       const int mt = job / NTL, nt = job - mt * NTL;
       const int m0 = mt * 32, n0 = nt * 32;
-      __syncthreads();
-      stage_kc(st, R1, a.W2, H, n0, 0, H);
-      st.commit();
+      if (job != cta) {
+        __syncthreads();
+        stage_kc(st, R1, a.W2, H, n0, 0, H);
+        st.commit();
+      }
       if (!(job == cta && xs_ready)) {
         if (tid < 32) sidx[tid] = a.perm[(cursor0 + s) * (long long)B + m0 + tid];
         __syncthreads();
@@ -366,45 +412,52 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         if (tid < 32) a.cur_idx[m0 + tid] = sidx[tid];
         for (int e = tid; e < 32 * D; e += NT) { const int r = e / D, i = e - r * D; a.xg[(size_t)(m0 + r) * D + i] = xs[r * MAXD + i]; }
       }
-      float whr[MAXO];
-#pragma unroll
-      for (int o = 0; o < MAXO; ++o) whr[o] = o < nout ? ldcg(ht.w[o] + n0 + lane) : 0.f;
-      const float b2v = ldcg(a.b2 + n0 + lane);
       {
-        // h1 panel: thread = 4 adjacent hidden units x 16 rows
-        const int k = (tid & 127) * 4, rh = tid >> 7;
-        if (k < H) {
-          float w[4][MAXD];
+        // h1 panel: warp = (row half, block of 128 hidden units); thread = units 128 kw + 32 j + lane, j < 4, x 16 rows
+        const int rh = warp >> 2, kbase = (warp & 3) * 128 + lane;
+        const float* W1s = R2;
+        const float* b1s = PS + (MAXO + 1) * PK;
+        float h[16][4];
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
+        for (int r = 0; r < 16; ++r)
 #pragma unroll
-            for (int i = 0; i < MAXD; ++i) w[kk][i] = i < D ? ldcg(a.W1 + (size_t)(k + kk) * D + i) : 0.f;
-          const float4 bb = ldcg4(a.b1 + k);
-#pragma unroll 4
+          for (int j = 0; j < 4; ++j) h[r][j] = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < D; ++i) {
+          float w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w[j] = kbase + 32 * j < H ? W1s[(kbase + 32 * j) * D + i] : 0.f;
+#pragma unroll
           for (int r = 0; r < 16; ++r) {
-            const int row = rh * 16 + r;
-            float xr[MAXD];
+            const float x = xs[(rh * 16 + r) * MAXD + i];
 #pragma unroll
-            for (int i4 = 0; i4 < MAXD / 4; ++i4) {
-              if (i4 * 4 < D) {
-                const float4 t = *reinterpret_cast<const float4*>(&xs[row * MAXD + i4 * 4]);
-                xr[i4 * 4] = t.x; xr[i4 * 4 + 1] = t.y; xr[i4 * 4 + 2] = t.z; xr[i4 * 4 + 3] = t.w;
-              } else { xr[i4 * 4] = xr[i4 * 4 + 1] = xr[i4 * 4 + 2] = xr[i4 * 4 + 3] = 0.f; }
+            for (int j = 0; j < 4; ++j) h[r][j] = fmaf(x, w[j], h[r][j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = kbase + 32 * j;
+          if (k < H) {
+            const float bb = b1s[k];
+            float* ps = R0 + rh * 16 * (H + 4) + k;
+            float* pgl = a.h1 + ((size_t)(k >> 5) * B + m0 + rh * 16) * 32 + (k & 31);   // tiled [H/32][B][32]
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const float hv = fmaxf(h[r][j] + bb, 0.f);
+              h[r][j] = hv;
+              ps[r * (H + 4)] = hv;
             }
-            float h[4] = {0.f, 0.f, 0.f, 0.f};
+            if (nt == 0) {
 #pragma unroll
-            for (int i = 0; i < MAXD; ++i) {
-              if (i < D) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) h[kk] = fmaf(xr[i], w[kk][i], h[kk]);
-              }
+              for (int r = 0; r < 16; ++r) pgl[r * 32] = h[r][j];
             }
-            const float4 hv = make_float4(fmaxf(h[0] + bb.x, 0.f), fmaxf(h[1] + bb.y, 0.f), fmaxf(h[2] + bb.z, 0.f), fmaxf(h[3] + bb.w, 0.f));
-            *reinterpret_cast<float4*>(&R0[row * (H + 4) + k]) = hv;
-            if (nt == 0) *reinterpret_cast<float4*>(&a.h1[((size_t)(k >> 5) * B + m0 + row) * 32 + (k & 31)]) = hv;   // tiled [H/32][B][32]
           }
         }
       }
+      float whr[MAXO];
+#pragma unroll
+      for (int o = 0; o < MAXO; ++o) whr[o] = o < nout ? PS[o * PK + n0 + lane] : 0.f;
+      const float b2v = PS[MAXO * PK + n0 + lane];
       TR(1);
       st.wait();
       __syncthreads();
@@ -417,29 +470,29 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       tile_reduce<true, true>(acc, R0, outv);
       TR(4);
       {
-        float hp_[4][MAXO];                                  // 4 rows x nout products, butterflies interleaved
+        // 32 per-lane values (4 rows x MAXO products) -> lane l ends with the warp total of value l: a butterfly
+        // that halves the value count at every step (31 shuffles, fixed order) instead of 5 shuffles per value
+        float hv_[32];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const float v = fmaxf(outv[r] + b2v, 0.f);
           a.h2[(size_t)(m0 + warp + 8 * r) * H + n0 + lane] = v;   // e = tid + r*256 -> (m = e >> 5, n = lane)
           a.h2t[((size_t)nt * B + m0 + warp + 8 * r) * 32 + lane] = v;   // and the tiled copy [H/32][B][32]
 #pragma unroll
-          for (int o = 0; o < MAXO; ++o) hp_[r][o] = v * whr[o];
+          for (int o = 0; o < MAXO; ++o) hv_[r * MAXO + o] = v * whr[o];
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
+        for (int off = 16, n = 16; off > 0; off >>= 1, n >>= 1) {
+          const bool up = (lane & off) != 0;
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int o = 0; o < MAXO; ++o)
-              if (o < nout) hp_[r][o] += __shfl_xor_sync(0xffffffffu, hp_[r][o], off);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          float mine = 0.f;
-#pragma unroll
-          for (int o = 0; o < MAXO; ++o) if (lane == o && o < nout) mine = hp_[r][o];
-          if (lane < 4 * nq) a.headp[(((size_t)nt * 2 + (lane >> 2)) * B + m0 + warp + 8 * r) * 4 + (lane & 3)] = mine;
+          for (int q = 0; q < n; ++q) {
+            const float keep = up ? hv_[q + n] : hv_[q], send = up ? hv_[q] : hv_[q + n];
+            hv_[q] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
         }
+        TR(35);
+        const int r = lane >> 3, o = lane & 7;               // lane l holds value l = r * MAXO + o
+        if (o < 4 * nq) a.headp[(((size_t)nt * 2 + (o >> 2)) * B + m0 + warp + 8 * r) * 4 + (o & 3)] = o < nout ? hv_[0] : 0.f;
       }
     }
     xs_ready = false;
@@ -461,12 +514,14 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
 #pragma unroll 1
       for (int b = tid; b < B; b += NT) {
         {
-          const int r = a.perm[(cursor0 + s) * (long long)B + b];
+          const float* d = dsm + b * MAXO;                    // parked in P1: adv, ret, v_old, log_prob_old, action, row id
+          const float g_adv = d[0], g_ret = d[1], g_vold = d[2], g_lpo = d[3];
+          const int g_act = __float_as_int(d[4]), r = __float_as_int(d[5]);
           float ov[2 * jbppo::MAX_A + 1];                     // row() indexes up to 2*MAX_A statically
 #pragma unroll
           for (int o = 0; o < 2 * jbppo::MAX_A + 1; ++o) ov[o] = 0.f;
 #pragma unroll
-          for (int o = 0; o < MAXO; ++o) if (o < nout) ov[o] = ldcg(ht.b[o]);
+          for (int o = 0; o < MAXO; ++o) if (o < nout) ov[o] = hb[o];
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             if (q < nq) {                                    // 16 independent loads in flight, folded in tile order
@@ -480,13 +535,13 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
               }
             }
           }
+          TR(31);
           jbppo::RowOut ro;
           if (a.continuous)
-            jbppo::row<true>(ov, A, 0, (const float*)a.action + (size_t)r * A, a.adv[r], a.ret[r], a.vold[r],
+            jbppo::row<true>(ov, A, 0, (const float*)a.action + (size_t)r * A, g_adv, g_ret, g_vold,
                              a.logp_old + (size_t)r * A, hp, invB, ro);
           else
-            jbppo::row<false>(ov, A, ((const int32_t*)a.action)[r], nullptr, a.adv[r], a.ret[r], a.vold[r],
-                              a.logp_old + r, hp, invB, ro);
+            jbppo::row<false>(ov, A, g_act, nullptr, g_adv, g_ret, g_vold, &g_lpo, hp, invB, ro);
 #pragma unroll
           for (int o = 0; o < MAXO; ++o) dsm[b * MAXO + o] = o < npol ? ro.dpol[o] : 0.f;
           dsm[b * MAXO + npol] = ro.dv1; dvs[b] = ro.dv2;      // the two candidate value-head gradients, resolved below
@@ -494,6 +549,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           mr = fmaxf(mr, ro.ratio); mp = fminf(mp, ro.pmin);
         }
       }
+      TR(32);
       p1 = jb_warp_sum(p1); p2 = jb_warp_sum(p2); ssum = jb_warp_sum(ssum); esum = jb_warp_sum(esum);
       mr = jb_warp_max(mr); mp = jb_warp_min(mp);
       if (lane == 0) { float* q = scr + warp * 8; q[0] = p1; q[1] = p2; q[2] = ssum; q[3] = esum; q[4] = mr; q[5] = mp; }
@@ -533,11 +589,14 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         const int c4 = (tid & 127) * 4, rh = tid >> 7;
         float4 wr[MAXO];
 #pragma unroll
-        for (int o = 0; o < MAXO; ++o) wr[o] = (o < nout && c4 < H) ? ldcg4(ht.w[o] + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[e] = i < D ? ldcg(a.xg + (size_t)(m0 + r) * D + i) : 0.f; }
-        float h1m[4];
+        for (int o = 0; o < MAXO; ++o)
+          wr[o] = (o < nout && c4 < H) ? *reinterpret_cast<const float4*>(&PS[o * PK + c4]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(job == cta && nJ1 <= (int)nctas))    // else xs still holds these rows from this CTA's P1 tile
+          for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[e] = i < D ? ldcg(a.xg + (size_t)(m0 + r) * D + i) : 0.f; }
+        float h1m[4];                              // relu mask of the output tile: asm volatile keeps the loads HERE
 #pragma unroll
-        for (int r = 0; r < 4; ++r) h1m[r] = ldcg(a.h1 + ((size_t)kt * B + m0 + warp + 8 * r) * 32 + lane);
+        for (int r = 0; r < 4; ++r)
+          asm volatile("ld.global.cg.f32 %0, [%1];\n" : "=f"(h1m[r]) : "l"(a.h1 + ((size_t)kt * B + m0 + warp + 8 * r) * 32 + lane));
         st.wait();
         TR(12);
         if (c4 < H) {
@@ -573,6 +632,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
 #pragma unroll
         for (int i = 0; i <= MAXD; ++i) if (i < D || i == MAXD) R0[(warp * (MAXD + 1) + i) * 32 + lane] = wacc[i];
         __syncthreads();
+        TR(33);
         for (int e = tid; e < 32 * (D + 1); e += NT) {
           const int n = e / (D + 1), i = e - n * (D + 1);
           const int slot = i < D ? i : MAXD;
@@ -582,6 +642,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           a.w1p[((size_t)mt * H + k0) * (D + 1) + e] = t;
         }
         __syncthreads();
+        TR(34);
         if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(a.barrier + CTR_JB + kt) : "memory");
         TR(16);
       } else if (job < nJB + nJA) {
@@ -592,7 +653,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         const int cg = tid & 7, rl = tid >> 3;
         float4 wr[MAXO];
 #pragma unroll
-        for (int o = 0; o < MAXO; ++o) wr[o] = o < nout ? ldcg4(ht.w[o] + n0 + 4 * cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int o = 0; o < MAXO; ++o) wr[o] = o < nout ? *reinterpret_cast<const float4*>(&PS[o * PK + n0 + 4 * cg]) : make_float4(0.f, 0.f, 0.f, 0.f);
         const int nhalf = (kt0 + 1 < NTL) ? 2 : 1;
         for (int half = 0; half < nhalf; ++half) {
           const int kt = kt0 + half, k0 = kt * 32;
@@ -754,10 +815,16 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
 #pragma unroll
         for (int q = 0; q < 2; ++q) { const int e = tid + q * NT, r = e >> 4, i = e & 15; if (i < D) xv[q] = a.state[(size_t)sidx[r] * D + i]; }
       }
-      // ||g||: every warp folds all partials in the same fixed order (no shared memory, no CTA barrier)
+      // ||g||: one coalesced read of the partials per CTA, then every warp folds them in the same fixed order
+      if (tid < (int)nctas) dvs[tid] = ldcg(a.partials + tid);
+      if (s + 1 < a.n_steps) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) pr[q] = tid + q * NT < B ? a.perm[(cursor0 + s + 1) * (long long)B + tid + q * NT] : 0;
+      }
+      __syncthreads();
       float pv[NT / 32];
 #pragma unroll
-      for (int q = 0; q < NT / 32; ++q) pv[q] = lane + 32 * q < (int)nctas ? ldcg(a.partials + lane + 32 * q) : 0.f;
+      for (int q = 0; q < NT / 32; ++q) pv[q] = lane + 32 * q < (int)nctas ? dvs[lane + 32 * q] : 0.f;
       double t = 0.0;
 #pragma unroll
       for (int q = 0; q < NT / 32; ++q) t += (double)pv[q];
@@ -813,7 +880,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
 }
 
 static int dsm_floats_for(int B) { return B * MAXO; }
-static size_t fused_smem(int B) { return sizeof(float) * (size_t)(SMALL_FLOATS + dsm_floats_for(B) + 2 * RED_FLOATS + R2_FLOATS); }
+static size_t fused_smem(int B) { return sizeof(float) * (size_t)(SMALL_FLOATS + dsm_floats_for(B) + 2 * RED_FLOATS + R2_FLOATS + PS_FLOATS); }
 
 // Largest grid the cooperative launch can keep co-resident (one CTA per SM on B200) for minibatch size B.
 static int fused_max_ctas(int B) {
@@ -833,9 +900,9 @@ JB_API int jb_ppo_fused_args_size(void) { return (int)sizeof(jb_ppo_fused_args);
 
 JB_API int jb_ppo_fused_max_ctas(void) { return fused_max_ctas(256); }
 
-// Debug: copy the clock64 trace of the last step (JB_FUSED_SKIP=256) to host memory: [256 CTAs][32 slots].
+// Debug: copy the clock64 trace of the last step (JB_FUSED_SKIP=256) to host memory: [256 CTAs][48 slots].
 JB_API int jb_ppo_fused_trace(long long* host_out) {
-  return cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 256 * 32) == cudaSuccess ? JB_OK : JB_ERR_CUDA;
+  return cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 256 * 48) == cudaSuccess ? JB_OK : JB_ERR_CUDA;
 }
 
 // Runs args->n_steps minibatch steps starting at the device-side cursor.  `args` is a HOST pointer to
