@@ -344,6 +344,20 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   int pr[2];
 #pragma unroll
   for (int q = 0; q < 2; ++q) pr[q] = tid + q * NT < B ? a.perm[cursor0 * (long long)B + tid + q * NT] : 0;
+  // ... and their rollout values (adv, ret, v_old, log_prob_old, action): gathered one phase ahead (every row is
+  // visited once per epoch, so these are cold misses), parked in dsm at the start of P1
+  float pg[2][5];
+  auto gather_rows = [&]() {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (tid + q * NT < B) {
+        const int r = pr[q];
+        pg[q][0] = a.adv[r]; pg[q][1] = a.ret[r]; pg[q][2] = a.vold[r];
+        if (!a.continuous) { pg[q][3] = a.logp_old[r]; pg[q][4] = __int_as_float(((const int32_t*)a.action)[r]); }
+      }
+    }
+  };
+  gather_rows();
   // state rows of this CTA's first P1 tile of step 0 (later steps: gathered under the Adam phase)
   bool xs_ready = false;
   if (cta < nJ1) {
@@ -359,29 +373,16 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
     TR(0);
     __syncthreads();                               // (step 0: the prologue; later steps: a no-op after the barrier)
     // =========================== P1: h2 = relu(relu(x W1^T + b1) W2^T + b2), partial head outputs ========
-    // rollout values of this thread's rows: issued first, parked in dsm (dead until the row phase) below
-    float pg[2][5];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      if (tid + q * NT < B) {
-        const int r = pr[q];
-        pg[q][0] = a.adv[r]; pg[q][1] = a.ret[r]; pg[q][2] = a.vold[r];
-        if (!a.continuous) { pg[q][3] = a.logp_old[r]; pg[q][4] = __int_as_float(((const int32_t*)a.action)[r]); }
-      }
-    }
-    if (cta < nJ1) { stage_kc(st, R1, a.W2, H, (cta % NTL) * 32, 0, H); st.commit(); }
-    // parameter stash: ONE bulk request per tensor per CTA.  (Per-thread loads of W1 / b1 / b2 / head rows had
-    // every warp of every CTA hit the same few KB right after the barrier: > 500 K sector requests queued on
-    // ~100 L2 lines, 4-5 us before the first value arrived.)
-    if (tid == 0) {
-      stp.copy(R2, a.W1, (unsigned)(H * D) * 4u);
-      stp.copy(PS + (MAXO + 1) * PK, a.b1, (unsigned)H * 4u);
-      stp.copy(PS + MAXO * PK, a.b2, (unsigned)H * 4u);
-      for (int o = 0; o < nout; ++o) stp.copy(PS + o * PK, ht.w[o], (unsigned)H * 4u);
-    }
-    if (tid >= 32 && tid < 32 + nout) hb[tid - 32] = ldcg(ht.b[tid - 32]);   // not warp 0: it must reach the arrive below
+    // parameter stash: ONE bulk request per tensor per CTA, issued from different warps.  (Per-thread loads of
+    // W1 / b1 / b2 / head rows had every warp of every CTA hit the same few KB right after the barrier: > 500 K
+    // sector requests queued on ~100 L2 lines, 4-5 us before the first value arrived.)
     stp.bytes = (unsigned)(H * D + (2 + nout) * H) * 4u;
-    stp.commit();
+    stp.commit();                                  // thread 0 arrives with the byte count before anything else
+    if (tid == 32) stp.copy(R2, a.W1, (unsigned)(H * D) * 4u);
+    if (tid == 64) { stp.copy(PS + (MAXO + 1) * PK, a.b1, (unsigned)H * 4u); stp.copy(PS + MAXO * PK, a.b2, (unsigned)H * 4u); }
+    if (tid >= 96 && tid < 96 + nout) stp.copy(PS + (tid - 96) * PK, ht.w[tid - 96], (unsigned)H * 4u);
+    if (tid >= 128 && tid < 128 + nout) hb[tid - 128] = ldcg(ht.b[tid - 128]);
+    if (cta < nJ1) { stage_kc(st, R1, a.W2, H, (cta % NTL) * 32, 0, H); st.commit(); }
     TR(28);
     stp.wait();
     TR(29);
@@ -413,44 +414,34 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         for (int e = tid; e < 32 * D; e += NT) { const int r = e / D, i = e - r * D; a.xg[(size_t)(m0 + r) * D + i] = xs[r * MAXD + i]; }
       }
       {
-        // h1 panel: warp = (row half, block of 128 hidden units); thread = units 128 kw + 32 j + lane, j < 4, x 16 rows
+        // h1 panel: warp = (row half, block of 128 hidden units); thread = units 128 kw + 32 j + lane, j < 4, x 16 rows.
+        // One compact loop body per unit (the fully unrolled form was ~2000 instructions executed once per step:
+        // instruction-fetch bound).
         const int rh = warp >> 2, kbase = (warp & 3) * 128 + lane;
         const float* W1s = R2;
         const float* b1s = PS + (MAXO + 1) * PK;
-        float h[16][4];
-#pragma unroll
-        for (int r = 0; r < 16; ++r)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) h[r][j] = 0.f;
+        const float* xrow = xs + rh * 16 * MAXD;
 #pragma unroll 1
-        for (int i = 0; i < D; ++i) {
-          float w[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) w[j] = kbase + 32 * j < H ? W1s[(kbase + 32 * j) * D + i] : 0.f;
-#pragma unroll
-          for (int r = 0; r < 16; ++r) {
-            const float x = xs[(rh * 16 + r) * MAXD + i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) h[r][j] = fmaf(x, w[j], h[r][j]);
-          }
-        }
-#pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = kbase + 32 * j;
-          if (k < H) {
-            const float bb = b1s[k];
-            float* ps = R0 + rh * 16 * (H + 4) + k;
+          if (k >= H) break;
+          float h[16];
+#pragma unroll
+          for (int r = 0; r < 16; ++r) h[r] = 0.f;
+#pragma unroll 1
+          for (int i = 0; i < D; ++i) {
+            const float w = W1s[k * D + i];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) h[r] = fmaf(xrow[r * MAXD + i], w, h[r]);
+          }
+          const float bb = b1s[k];
+          float* ps = R0 + rh * 16 * (H + 4) + k;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) { h[r] = fmaxf(h[r] + bb, 0.f); ps[r * (H + 4)] = h[r]; }
+          if (nt == 0) {
             float* pgl = a.h1 + ((size_t)(k >> 5) * B + m0 + rh * 16) * 32 + (k & 31);   // tiled [H/32][B][32]
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-              const float hv = fmaxf(h[r][j] + bb, 0.f);
-              h[r][j] = hv;
-              ps[r * (H + 4)] = hv;
-            }
-            if (nt == 0) {
-#pragma unroll
-              for (int r = 0; r < 16; ++r) pgl[r * 32] = h[r][j];
-            }
+            for (int r = 0; r < 16; ++r) pgl[r * 32] = h[r];
           }
         }
       }
@@ -507,6 +498,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
     const bool has_next = (s + 1 < a.n_steps) && cta < nJ1;
     int next_r = 0;
     if (has_next && tid < 32) next_r = a.perm[(cursor0 + s + 1) * (long long)B + (cta / NTL) * 32 + tid];
+    if (s + 1 < a.n_steps) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) pr[q] = tid + q * NT < B ? a.perm[(cursor0 + s + 1) * (long long)B + tid + q * NT] : 0;
+    }
 
     float c1, c2;
     {
@@ -817,10 +812,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       }
       // ||g||: one coalesced read of the partials per CTA, then every warp folds them in the same fixed order
       if (tid < (int)nctas) dvs[tid] = ldcg(a.partials + tid);
-      if (s + 1 < a.n_steps) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) pr[q] = tid + q * NT < B ? a.perm[(cursor0 + s + 1) * (long long)B + tid + q * NT] : 0;
-      }
+      if (s + 1 < a.n_steps) gather_rows();        // next step's rollout values (row ids were loaded in P3)
       __syncthreads();
       float pv[NT / 32];
 #pragma unroll
