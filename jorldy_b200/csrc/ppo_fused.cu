@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   float* R1 = R0 + RED_FLOATS;                 // RED_FLOATS: B panels
   float* R2 = R1 + RED_FLOATS;                 // R2_FLOATS:  A panel of JA / JC; W1 during P1
   float* PS = R2 + R2_FLOATS;                  // PS_FLOATS:  head weight rows, b2, b1 of the current step
-  float* xs = s_small;                         // [32][MAXD] state rows of the current tile (zero padded)
+  float* xs = s_small;                         // [MAXD][32] state rows of the current tile, transposed (zero padded)
   float* scr = s_small + 768;                  // reduction scratch [128]
   int* sidx = reinterpret_cast<int*>(s_small + 1024);   // [32] gathered rollout row ids of the P1 tile
   Stager st;
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   if (cta < nJ1) {
     if (tid < 32) sidx[tid] = a.perm[cursor0 * (long long)B + (cta / NTL) * 32 + tid];
     __syncthreads();
-    for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[e] = i < D ? a.state[(size_t)sidx[r] * D + i] : 0.f; }
+    for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[i * 32 + r] = i < D ? a.state[(size_t)sidx[r] * D + i] : 0.f; }
     xs_ready = true;
   }
   __syncthreads();
@@ -406,12 +406,12 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       if (!(job == cta && xs_ready)) {
         if (tid < 32) sidx[tid] = a.perm[(cursor0 + s) * (long long)B + m0 + tid];
         __syncthreads();
-        for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[e] = i < D ? a.state[(size_t)sidx[r] * D + i] : 0.f; }
+        for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[i * 32 + r] = i < D ? a.state[(size_t)sidx[r] * D + i] : 0.f; }
         __syncthreads();
       }
       if (nt == 0) {
         if (tid < 32) a.cur_idx[m0 + tid] = sidx[tid];
-        for (int e = tid; e < 32 * D; e += NT) { const int r = e / D, i = e - r * D; a.xg[(size_t)(m0 + r) * D + i] = xs[r * MAXD + i]; }
+        for (int e = tid; e < 32 * D; e += NT) { const int r = e / D, i = e - r * D; a.xg[(size_t)(m0 + r) * D + i] = xs[i * 32 + r]; }
       }
       {
         // h1 panel: warp = (row half, block of 128 hidden units); thread = units 128 kw + 32 j + lane, j < 4, x 16 rows.
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         const int rh = warp >> 2, kbase = (warp & 3) * 128 + lane;
         const float* W1s = R2;
         const float* b1s = PS + (MAXO + 1) * PK;
-        const float* xrow = xs + rh * 16 * MAXD;
+        const float* xcol = xs + rh * 16;          // x[i][rh*16 .. +16): four LDS.128 per input feature
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           const int k = kbase + 32 * j;
@@ -432,7 +432,11 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           for (int i = 0; i < D; ++i) {
             const float w = W1s[k * D + i];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) h[r] = fmaf(xrow[r * MAXD + i], w, h[r]);
+            for (int r4 = 0; r4 < 4; ++r4) {
+              const float4 x = *reinterpret_cast<const float4*>(&xcol[i * 32 + r4 * 4]);
+              h[r4 * 4] = fmaf(x.x, w, h[r4 * 4]); h[r4 * 4 + 1] = fmaf(x.y, w, h[r4 * 4 + 1]);
+              h[r4 * 4 + 2] = fmaf(x.z, w, h[r4 * 4 + 2]); h[r4 * 4 + 3] = fmaf(x.w, w, h[r4 * 4 + 3]);
+            }
           }
           const float bb = b1s[k];
           float* ps = R0 + rh * 16 * (H + 4) + k;
@@ -522,8 +526,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
             if (q < nq) {                                    // 16 independent loads in flight, folded in tile order
               float4 v[PK / 32];
 #pragma unroll
-              for (int nt = 0; nt < PK / 32; ++nt)
-                v[nt] = nt < NTL ? ldcg4(a.headp + (((size_t)nt * 2 + q) * B + b) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int nt = 0; nt < PK / 32; ++nt)      // clamped, not predicated: all 16 loads go out back to back
+                v[nt] = ldcg4(a.headp + (((size_t)min(nt, NTL - 1) * 2 + q) * B + b) * 4);
 #pragma unroll
               for (int nt = 0; nt < PK / 32; ++nt) {
                 if (nt < NTL) { ov[q * 4] += v[nt].x; ov[q * 4 + 1] += v[nt].y; ov[q * 4 + 2] += v[nt].z; ov[q * 4 + 3] += v[nt].w; }
@@ -587,7 +591,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         for (int o = 0; o < MAXO; ++o)
           wr[o] = (o < nout && c4 < H) ? *reinterpret_cast<const float4*>(&PS[o * PK + c4]) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (!(job == cta && nJ1 <= (int)nctas))    // else xs still holds these rows from this CTA's P1 tile
-          for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[e] = i < D ? ldcg(a.xg + (size_t)(m0 + r) * D + i) : 0.f; }
+          for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[i * 32 + r] = i < D ? ldcg(a.xg + (size_t)(m0 + r) * D + i) : 0.f; }
         float h1m[4];                              // relu mask of the output tile: asm volatile keeps the loads HERE
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -619,9 +623,9 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const float dv = h1m[r] > 0.f ? outv[r] : 0.f;
-          const float* xrow = &xs[(warp + 8 * r) * MAXD];
+          const float* xrow = &xs[warp + 8 * r];
 #pragma unroll
-          for (int i = 0; i < MAXD; ++i) if (i < D) wacc[i] = fmaf(dv, xrow[i], wacc[i]);
+          for (int i = 0; i < MAXD; ++i) if (i < D) wacc[i] = fmaf(dv, xrow[i * 32], wacc[i]);
           wacc[MAXD] += dv;
         }
 #pragma unroll
@@ -860,7 +864,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       }
       if (has_next) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) xs[tid + q * NT] = xv[q];
+        for (int q = 0; q < 2; ++q) { const int e = tid + q * NT; xs[(e & 15) * 32 + (e >> 4)] = xv[q]; }
         xs_ready = true;
       }
     }
