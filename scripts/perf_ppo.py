@@ -28,6 +28,7 @@ print(f"total   {t_col+t_learn:.2f} ms -> {N*T/(t_col+t_learn)/1e3:.3f} M env-st
 print("episodes finished:", env.stats.tolist())
 # per-minibatch step time
 st = agent._st
+agent._cursor.zero_()     # learn() left the cursor at the end of the permutation
 g = agent._graph_for(st, B)
 agent._cursor.zero_()
 t_g = timed(lambda: (agent._cursor.zero_(), g.replay()), n=20)

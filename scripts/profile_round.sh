@@ -17,5 +17,10 @@ tail -c 600 gpurun_out/bench_ref_$R.json
 N_ENVS=4096 T=128 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_bench_$R.csv python scripts/ncu_ppo.py > gpurun_out/ncu_list_$R.log 2>&1
 tail -1 gpurun_out/ncu_list_$R.log
 # full capture of the dominant kernel at bench shape (2048 steps/launch)
-T=128 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ppo_epoch -c 1 -o gpurun_out/ppo_epoch_$R python scripts/perf_phases.py child > gpurun_out/ncu_full_$R.log 2>&1
+T=128 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ppo_epoch -c 1 -o gpurun_out/ppo_epoch_$R python scripts/ncu_fused.py > gpurun_out/ncu_full_$R.log 2>&1
 tail -2 gpurun_out/ncu_full_$R.log
+# per-kernel DRAM traffic + headline numbers of that capture
+ncu -i gpurun_out/ppo_epoch_$R.ncu-rep --page raw --csv --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread,smsp__inst_executed.sum > gpurun_out/ppo_epoch_raw_$R.csv 2>/dev/null
+tail -3 gpurun_out/ppo_epoch_raw_$R.csv
+timeout 120 python scripts/perf_trace.py > gpurun_out/trace_$R.txt 2>&1; head -3 gpurun_out/trace_$R.txt
+timeout 300 python scripts/perf_ppo.py 2>&1 | tail -6
