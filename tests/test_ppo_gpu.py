@@ -88,6 +88,42 @@ def test_ppo_fused_equals_multilaunch_path():
         np.testing.assert_allclose(r1[k], r2[k], rtol=1e-4, atol=1e-5, err_msg=k)
 
 
+# shapes that exercise the generic paths of the persistent kernel the golden cases do not reach
+_FUSED_SHAPES = {
+    # B > 256: panels in 256-row chunks, JA pairs not shared; 256 forward tiles > 148 CTAs: several tiles per CTA
+    "b512_h512": dict(seed=21, N=16, T=128, D=4, A=2, H=512, continuous=False, batch_size=512, n_epoch=1),
+    # odd number of column tiles (H/32 = 3): the last dW2 pair has one member; tiny grid of jobs
+    "b64_h96_cont": dict(seed=22, N=4, T=64, D=3, A=1, H=96, continuous=True, batch_size=64, n_epoch=2),
+    # D = 16 (widest input the kernel takes), A = 7 (nout = 8: both head-output quads)
+    "b128_h256_d16_a7": dict(seed=23, N=8, T=64, D=16, A=7, H=256, continuous=False, batch_size=128, n_epoch=1),
+    # ragged tail: 1000 rows = 3 x 256 + 232 -> the tail minibatch takes the multi-launch path after the fused launch
+    "b256_tail": dict(seed=24, N=8, T=125, D=4, A=2, H=128, continuous=False, batch_size=256, n_epoch=2),
+}
+
+
+@pytest.mark.parametrize("name", list(_FUSED_SHAPES.keys()))
+def test_ppo_fused_generic_shapes_equal_multilaunch(name):
+    case = dict(lr=2.5e-4, gamma=0.99, lam=0.95, eps_clip=0.1, vf_coef=1.0, ent_coef=0.01, clip_grad_norm=1.0,
+                standardize=True, **_FUSED_SHAPES[name])
+    a1, r1, _ = _run_cuda(case, False, use_fused=True)
+    assert a1._fused, "fused path was not taken"
+    a2, r2, _ = _run_cuda(case, False, use_fused=False)
+    assert not a2._fused
+    for k in a1.network.p:
+        np.testing.assert_allclose(a1.network.p[k].cpu().numpy(), a2.network.p[k].cpu().numpy(), rtol=1e-4,
+                                   atol=0.02 * case["lr"], err_msg=k)
+    for k in r1:
+        np.testing.assert_allclose(r1[k], r2[k], rtol=2e-4, atol=2e-5, err_msg=k)
+
+
+def test_ppo_fused_is_bit_reproducible():
+    """Static job maps + fixed-order reductions: two runs give identical bits."""
+    case = G.PPO_CASES["ppo_discrete_h512"]
+    a1, _, _ = _run_cuda(case, False, use_fused=True)
+    a2, _, _ = _run_cuda(case, False, use_fused=True)
+    assert torch.equal(a1.network.flat, a2.network.flat)
+
+
 @pytest.mark.parametrize("name", ["ppo_discrete_small", "ppo_continuous_small", "ppo_discrete_h512"])
 def test_ppo_first_minibatch_grads_match_oracle(name):
     case = dict(G.PPO_CASES[name])
