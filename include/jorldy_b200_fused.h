@@ -33,6 +33,13 @@ typedef struct jb_ppo_fused_args {
   long long *step;                   /* Adam step counter (device) */
   long long *cursor;                 /* minibatch cursor (device) */
   const float *lr;                   /* learning rate (device scalar) */
+  /* multi-GPU: gradient exchange through peer-mapped memory (world == 1: unused).  peer[r] = rank r's exchange
+   * buffer (the flat gradient followed by >= 256 uint32 flag words at float offset xflag_off); `grad` above is
+   * peer[rank].  Flags are monotonic: xbase = number of steps run by earlier launches. */
+  float *peer[8];
+  int world, rank;
+  unsigned int xbase;
+  int xflag_off;
   int nh[3];                         /* outputs per head */
   int B, D, H, A, nout, continuous, n_steps;
   float eps_clip, vf_coef, ent_coef, beta1, beta2, adam_eps, max_norm;

@@ -263,7 +263,9 @@ class PPO(BaseAgent):
         n_chunks = (NT + 16383) // 16384
         self.n_prepass_launches = 3 * n_chunks + 1 + 3 + 1      # forward chunks + prepass + V(s') + gae
 
-        acc = torch.cat([self._acc[:6], mean_ret.view(1)]).cpu().numpy()     # ONE device->host read
+        acc = torch.cat([self._acc[:6], mean_ret.view(1), self._acc[7:8]]).cpu().numpy()     # ONE device->host read
+        if acc[7] != 0.0:
+            raise RuntimeError("persistent PPO kernel: a peer GPU did not reach the gradient exchange (flag wait timed out)")
         cnt = max(acc[5], 1.0)
         return {
             "actor_loss": float(acc[0] / cnt),

@@ -17,6 +17,7 @@ class FusedArgs(ctypes.Structure):
         ("state", _P), ("action", _P), ("adv", _P), ("ret", _P), ("vold", _P), ("logp_old", _P), ("perm", _P),
         ("h1", _P), ("h2", _P), ("xg", _P), ("w1p", _P), ("headp", _P), ("h2t", _P), ("W2t", _P), ("partials", _P), ("acc", _P),
         ("cur_idx", _P), ("barrier", _P), ("step", _P), ("cursor", _P), ("lr", _P),
+        ("peer", _P * 8), ("world", ctypes.c_int), ("rank", ctypes.c_int), ("xbase", ctypes.c_uint), ("xflag_off", ctypes.c_int),
         ("nh", ctypes.c_int * 3),
         ("B", ctypes.c_int), ("D", ctypes.c_int), ("H", ctypes.c_int), ("A", ctypes.c_int), ("nout", ctypes.c_int),
         ("continuous", ctypes.c_int), ("n_steps", ctypes.c_int),
@@ -28,7 +29,8 @@ class FusedArgs(ctypes.Structure):
 def supported(agent, B):
     net = agent.network
     head = getattr(net, "head", None)
-    return (getattr(head, "kind", None) == "mlp" and type(agent.optimizer).__name__ == "Adam" and agent.allreduce is None
+    return (getattr(head, "kind", None) == "mlp" and type(agent.optimizer).__name__ == "Adam"
+            and (agent.allreduce is None or getattr(agent, "p2p", None) is not None)
             and B % 32 == 0 and B <= 512 and net.D_hidden % 32 == 0 and net.D_hidden <= 512 and head.D_in <= 16 and net.nout <= 8
             and head.D_head_out == net.D_hidden and agent.action_size <= 8)
 
@@ -79,4 +81,13 @@ class FusedRunner:
         a.eps_clip, a.vf_coef, a.ent_coef = ag.epsilon_clip, ag.vf_coef, ag.ent_coef
         a.beta1, a.beta2, a.adam_eps = opt.betas[0], opt.betas[1], opt.eps
         a.max_norm = float(ag.clip_grad_norm) if ag.clip_grad_norm else 0.0
+        p2p = getattr(ag, "p2p", None)
+        if p2p is not None:
+            assert net.grad.data_ptr() == p2p["ptrs"][p2p["rank"]], "gradient buffer is not the peer-mapped exchange buffer"
+            for r in range(8):
+                a.peer[r] = p2p["ptrs"][r] if r < p2p["world"] else None
+            a.world, a.rank, a.xbase, a.xflag_off = p2p["world"], p2p["rank"], p2p["epoch"] & 0xFFFFFFFF, p2p["flag_off"]
+            p2p["epoch"] += int(n_steps)
+        else:
+            a.world, a.rank, a.xbase, a.xflag_off = 1, 0, 0, 0
         C.jb_ppo_fused_run(ctypes.addressof(a), stream_ptr())

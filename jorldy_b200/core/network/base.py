@@ -58,6 +58,7 @@ class FlatNetwork:
         self.num_flat = total
         self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
         self.grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self._offs = offs
         self.p = OrderedDict()
         self.g = OrderedDict()
         for (name, shape), off in zip(self._specs, offs):
@@ -65,6 +66,19 @@ class FlatNetwork:
             for s in shape:
                 n *= s
             self.p[name] = self.flat[off:off + n].view(*shape)
+            self.g[name] = self.grad[off:off + n].view(*shape)
+
+    def rebind_grad(self, storage):
+        """Moves the flat gradient buffer into `storage` (a 1-D fp32 CUDA tensor of at least num_flat elements, e.g.
+        a peer-mapped symmetric-memory allocation for the in-kernel gradient exchange) and rebuilds the views."""
+        assert storage.dtype == torch.float32 and storage.numel() >= self.num_flat and storage.device == self.grad.device
+        new = storage[:self.num_flat]
+        new.copy_(self.grad)
+        self.grad = new
+        for (name, shape), off in zip(self._specs, self._offs):
+            n = 1
+            for s in shape:
+                n *= s
             self.g[name] = self.grad[off:off + n].view(*shape)
 
     def num_params(self):

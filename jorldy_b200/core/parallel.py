@@ -12,6 +12,37 @@ import torch
 import torch.distributed as dist
 
 
+P2P_FLAG_WORDS = 256     # uint32 flag words appended to the exchange buffer (zeroed before the rendezvous)
+
+
+def _try_p2p(agent, world_size):
+    """Peer-mapped gradient exchange buffer for the persistent PPO kernel (csrc/ppo_fused.cu): every rank's flat
+    gradient lives in a symmetric-memory allocation whose peer pointers the kernel reads over NVLink, so the
+    all-reduce happens INSIDE the kernel (peer loads + flag barrier) instead of 6144 NCCL calls per learn().
+    Falls back silently (agent.p2p = None -> CUDA graphs + NCCL) when symmetric memory is unavailable."""
+    agent.p2p = None
+    net = getattr(agent, "network", None)
+    if net is None or not net.flat.is_cuda or dist.get_backend() != "nccl" or world_size > 8 or type(agent).__name__ != "PPO":
+        return
+    try:
+        import torch.distributed._symmetric_memory as symm
+        n = net.num_flat + P2P_FLAG_WORDS
+        buf = symm.empty(n, dtype=torch.float32, device=net.flat.device)
+        buf.zero_()
+        torch.cuda.synchronize()
+        hdl = symm.rendezvous(buf, dist.group.WORLD)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        assert len(ptrs) == world_size
+        net.rebind_grad(buf)
+        dist.barrier()
+        agent.p2p = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "rank": dist.get_rank(), "world": world_size, "epoch": 0,
+                     "flag_off": net.num_flat}
+    except Exception as e:      # pragma: no cover - depends on the platform
+        import warnings
+        warnings.warn(f"in-kernel gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
+        agent.p2p = None
+
+
 def attach(agent, world_size, average_with="avg"):
     """Makes `agent` a data-parallel learner: identical initial weights on every rank (broadcast from
     rank 0) and an averaged flat gradient before every optimiser step."""
@@ -30,6 +61,7 @@ def attach(agent, world_size, average_with="avg"):
             flat_grad.div_(world_size)
 
     agent.allreduce = allreduce
+    _try_p2p(agent, world_size)
     mem = getattr(agent, "memory", None)
     if mem is not None and hasattr(mem, "sample_device") and hasattr(mem, "tree_size"):
         mem.shard_world = world_size            # PER tree becomes one shard of a world_size-way replay

@@ -102,6 +102,24 @@ struct Stager {
   }
 };
 
+// ---- cross-GPU flag wait (multi-GPU gradient exchange): bounded, so that a dead peer cannot hang this GPU
+__device__ __forceinline__ bool sys_flag_wait(const unsigned int* flag, unsigned int target) {
+  for (unsigned int it = 0; it < (1u << 25); ++it) {   // ~20-30 s of polling
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
+    if ((int)(v - target) >= 0) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void sys_flag_set(unsigned int* flag, unsigned int value) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(flag), "r"(value) : "memory");
+}
+__device__ __forceinline__ float4 ld_sys4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 // ---- grid barrier (all CTAs co-resident: cooperative launch) ------------------------------------------
 __device__ __forceinline__ void grid_bar(unsigned int* ctr, unsigned int& epoch, unsigned int nctas) {
   __syncthreads();                       // CTA scope: every thread's phase writes happen-before thread 0's release
@@ -496,6 +514,14 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
     TR(6);
 
     // =========================== P3: row phase + backward jobs =========================================
+    if (a.world > 1) {
+      // peers read this rank's gradient of the PREVIOUS step over NVLink: they must be done before it is rewritten
+      if (tid < a.world && tid != a.rank) {
+        const unsigned int* f2 = reinterpret_cast<const unsigned int*>(a.peer[a.rank] + a.xflag_off) + 64 + tid;
+        if (!sys_flag_wait(f2, a.xbase + (unsigned int)s)) a.acc[7] = 1.f;
+      }
+      __syncthreads();
+    }
     int pre_job = -1;                              // job whose first panels are already in flight
     if (cta < nJ3 && (cta < nJB || prefetchable(cta))) { issue_stage(cta); pre_job = cta; }
     // row ids of the NEXT step's first P1 tile: the load is in flight during the whole phase
@@ -784,7 +810,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       }
     }
     TR(22);
-    {
+    if (a.world == 1) {                            // (multi-GPU: the norm is taken of the AVERAGED gradient, below)
       const float tot = block_sum(sq, scr + 64);
       if (tid == 0) a.partials[cta] = tot;
     }
@@ -803,10 +829,52 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
     // =========================== P5: clip + Adam on this CTA's slice ===================================
     {
       float4 gg[ADAM_IT];
+      if (a.world == 1) {
 #pragma unroll
-      for (int it = 0; it < ADAM_IT; ++it) {
-        const long long i = lo + tid + it * NT;
-        if (i < hi) gg[it] = __ldcg(g4 + i);
+        for (int it = 0; it < ADAM_IT; ++it) {
+          const long long i = lo + tid + it * NT;
+          if (i < hi) gg[it] = __ldcg(g4 + i);
+        }
+      } else {
+        // ---- gradient all-reduce over peer memory (NVLink): flag barrier, then every CTA averages ITS slice of all
+        // ranks' gradients in rank order (identical bits everywhere), then the norm of the averaged gradient
+        const unsigned int target = a.xbase + (unsigned int)s + 1u;
+        if (tid < a.world && tid != a.rank) {
+          if (cta == 0) {                                            // this rank's gradient is complete (barrier above)
+            __threadfence_system();
+            sys_flag_set(reinterpret_cast<unsigned int*>(a.peer[tid] + a.xflag_off) + a.rank, target);
+          }
+          if (!sys_flag_wait(reinterpret_cast<const unsigned int*>(a.peer[a.rank] + a.xflag_off) + tid, target)) a.acc[7] = 1.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < ADAM_IT; ++it) gg[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int r = 0; r < a.world; ++r) {
+          const float* src = a.peer[r];
+          float4 t[ADAM_IT];
+#pragma unroll
+          for (int it = 0; it < ADAM_IT; ++it) {
+            const long long i = lo + tid + it * NT;
+            t[it] = i < hi ? ld_sys4(src + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int it = 0; it < ADAM_IT; ++it) { gg[it].x += t[it].x; gg[it].y += t[it].y; gg[it].z += t[it].z; gg[it].w += t[it].w; }
+        }
+        const float inv_world = 1.f / (float)a.world;
+        float sqa = 0.f;
+#pragma unroll
+        for (int it = 0; it < ADAM_IT; ++it) {
+          gg[it].x *= inv_world; gg[it].y *= inv_world; gg[it].z *= inv_world; gg[it].w *= inv_world;
+          sqa = fmaf(gg[it].x, gg[it].x, sqa); sqa = fmaf(gg[it].y, gg[it].y, sqa);
+          sqa = fmaf(gg[it].z, gg[it].z, sqa); sqa = fmaf(gg[it].w, gg[it].w, sqa);
+        }
+        const float tot = block_sum(sqa, scr + 64);
+        if (tid == 0) a.partials[cta] = tot;
+        grid_bar(a.barrier, epoch, nctas);
+        // every CTA of this rank has read the peers' gradients of this step: they may overwrite them
+        if (cta == 0 && tid < a.world && tid != a.rank)
+          sys_flag_set(reinterpret_cast<unsigned int*>(a.peer[tid] + a.xflag_off) + 64 + a.rank, target);
       }
       // next step's state rows (sidx was published before the barrier)
       float xv[2] = {0.f, 0.f};
@@ -912,6 +980,11 @@ JB_API int jb_ppo_fused_run(const void* host_args, void* stream) {
   int ctas = fused_max_ctas(a.B);
   if (ctas <= 0) return JB_ERR_INVALID;
   if (ctas > NT) ctas = NT;
+  if (a.world < 1 || a.world > 8 || a.rank < 0 || a.rank >= a.world) return JB_ERR_INVALID;
+  if (a.world > 1) {   // the exchange keeps a CTA's gradient slice in registers; grad must be this rank's exchange buffer
+    if (a.P4 > (long long)ctas * ADAM_IT * NT || a.peer[a.rank] != a.grad || a.xflag_off < a.P4 * 4) return JB_ERR_INVALID;
+    for (int r = 0; r < a.world; ++r) if (!a.peer[r]) return JB_ERR_INVALID;
+  }
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(a.barrier, 0, 64 * sizeof(unsigned int), s) != cudaSuccess) return JB_ERR_CUDA;   // grid counter + JB counters
   const size_t smem = fused_smem(a.B);
