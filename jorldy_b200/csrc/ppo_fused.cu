@@ -32,8 +32,15 @@
 // Determinism: static job -> CTA maps, fixed-order reductions, no float atomics: bit-reproducible run
 // to run.  Coherence: every buffer written inside the kernel is read with ld.global.cg / cp.async.cg
 // (L2), and the barrier's gpu-scope release/acquire orders the phases.
+//
+// Multi-GPU (args.world > 1): every rank's flat gradient lives in a peer-mapped exchange buffer (args.peer[r],
+// torch symmetric memory).  After the backward phase's barrier the kernel publishes a "gradient complete" flag to all
+// peers, waits for theirs, and every CTA reads ITS Adam slice of every rank's gradient over NVLink (rank order =>
+// identical bits everywhere), averages, and the clip norm is taken of the averaged gradient (one more grid barrier);
+// a second flag tells the peers their gradients may be overwritten.  No NCCL call between backward and Adam.
+//
 // Constraints (else the host uses the multi-launch path): B % 32 == 0, B <= 512, H % 32 == 0, H <= 512,
-// D <= 16, nout <= 8, single GPU (no gradient all-reduce between backward and Adam).
+// D <= 16, nout <= 8; multi-GPU additionally: <= 8 ranks, <= 8 K parameters per CTA slice (1.2 M parameters).
 #include <cstdlib>
 #include "common.cuh"
 #include "ppo_rowmath.cuh"

@@ -116,6 +116,31 @@ def test_ppo_fused_generic_shapes_equal_multilaunch(name):
         np.testing.assert_allclose(r1[k], r2[k], rtol=2e-4, atol=2e-5, err_msg=k)
 
 
+def test_rebind_grad_keeps_both_paths_working():
+    """parallel.attach() moves the flat gradient into a peer-mapped buffer (network.rebind_grad): every backward kernel
+    must follow the rebuilt views (no cached pointers)."""
+    case = G.PPO_CASES["ppo_discrete_h512"]
+    outs = []
+    for fused in (True, False):
+        params, batch, hp, perms = ppo_oracle_inputs(case)
+        agent = _make_agent(case, use_cuda_graph=False, use_fused=fused)
+        agent.network.load_state_dict(params)
+        new = torch.full((agent.network.num_flat + 256,), 7.0, device="cuda")
+        old_ptr = agent.network.grad.data_ptr()
+        agent.network.rebind_grad(new)
+        assert agent.network.grad.data_ptr() == new.data_ptr() != old_ptr
+        agent._inject_perms = perms
+        res = agent._learn_tensors(batch["state"].cuda(), batch["action"].reshape(-1).to(torch.int32).cuda(),
+                                   batch["reward"].reshape(-1).cuda(), batch["done"].reshape(-1).cuda(),
+                                   next_state=batch["next_state"].cuda())
+        torch.cuda.synchronize()
+        assert torch.all(new[agent.network.num_flat:] == 7.0), "wrote past the gradient region"
+        assert float(new[:agent.network.num_flat].abs().sum()) > 0, "gradients did not land in the new buffer"
+        gold = load_golden("ppo_discrete_h512")
+        params_after = {k: v.cpu().numpy() for k, v in agent.network.state_dict().items()}
+        check_against_golden(gold, params_after, res, None, rtol=1e-4, atol=0.1 * case["lr"], stat_tol=2e-4)
+
+
 def test_ppo_fused_is_bit_reproducible():
     """Static job maps + fixed-order reductions: two runs give identical bits."""
     case = G.PPO_CASES["ppo_discrete_h512"]
