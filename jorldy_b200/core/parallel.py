@@ -24,6 +24,7 @@ def _try_p2p(agent, world_size):
     net = getattr(agent, "network", None)
     if net is None or not net.flat.is_cuda or dist.get_backend() != "nccl" or world_size > 8 or type(agent).__name__ != "PPO":
         return
+    ok, buf, hdl, ptrs, err = 1, None, None, None, None
     try:
         import torch.distributed._symmetric_memory as symm
         n = net.num_flat + P2P_FLAG_WORDS
@@ -32,15 +33,21 @@ def _try_p2p(agent, world_size):
         torch.cuda.synchronize()
         hdl = symm.rendezvous(buf, dist.group.WORLD)
         ptrs = [int(p) for p in hdl.buffer_ptrs]
-        assert len(ptrs) == world_size
-        net.rebind_grad(buf)
-        dist.barrier()
-        agent.p2p = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "rank": dist.get_rank(), "world": world_size, "epoch": 0,
-                     "flag_off": net.num_flat}
+        if len(ptrs) != world_size or ptrs[dist.get_rank()] != buf.data_ptr():
+            raise RuntimeError("unexpected symmetric-memory pointer table")
     except Exception as e:      # pragma: no cover - depends on the platform
+        ok, err = 0, e
+    # the decision is collective: either every rank exchanges in-kernel or every rank uses NCCL
+    flag = torch.tensor([ok], dtype=torch.int32, device=net.flat.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) != 1:
         import warnings
-        warnings.warn(f"in-kernel gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
-        agent.p2p = None
+        warnings.warn(f"in-kernel gradient exchange unavailable ({type(err).__name__ if err else 'peer'}: {err}); using NCCL all-reduce")
+        return
+    net.rebind_grad(buf)
+    dist.barrier()
+    agent.p2p = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "rank": dist.get_rank(), "world": world_size, "epoch": 0,
+                 "flag_off": net.num_flat}
 
 
 def attach(agent, world_size, average_with="avg"):
