@@ -4,7 +4,9 @@
 A "step" = one full PPO iteration on every rank: collect T=128 steps of 4096 batched CartPole envs
 (policy forward + sampling + physics + rollout write, all on the GPU), then learn(): pre-pass,
 GAE, 3 epochs x (N*T/256) shuffled minibatch steps (forward, fused loss fwd+bwd, backward, global-norm
-clip, Adam).  `value` = env-steps/s over all ranks with the rollout resident in HBM; `e2e` = the same
+clip, Adam) — one launch of the persistent kernel per epoch; at N > 1 the per-step gradient average happens inside
+that kernel over NVLink peer memory (NCCL CUDA graphs if symmetric memory is unavailable).  `value` = env-steps/s
+over all ranks with the rollout resident in HBM; `e2e` = the same
 loop driven through the reference-shaped plugin API (agent.act / env.step / agent.process) with HOST
 numpy buffers, every host<->device copy inside the timed region.
 
@@ -50,6 +52,7 @@ def workload_config(world):
                         "(config.ppo.cartpole hyper-parameters, distributed_batch_size 256)",
             "n_envs_per_gpu": N_ENVS, "n_step": N_STEP, "batch_size_per_gpu": BATCH, "n_epoch": N_EPOCH,
             "hidden": HIDDEN, "parallelism": f"dp{world}",
+            "gradient_exchange": "none (1 GPU)" if world == 1 else "in-kernel peer-memory all-reduce per minibatch step (jorldy_b200/core/parallel.py)",
             "l2": "flushed between timed steps (256 MB fill, > 126 MB L2); every step re-collects its rollout"}
 
 
