@@ -24,6 +24,28 @@ def test_c_abi_exports_every_declared_symbol():
     load()
 
 
+def test_fused_args_struct_matches_its_ctypes_mirror():
+    """include/jorldy_b200_fused.h is mirrored field by field in core/agent/ppo_fused.py: sizes must agree (host-only call)."""
+    from jorldy_b200._lib import C
+    from jorldy_b200.core.agent.ppo_fused import FusedArgs
+    assert ctypes.sizeof(FusedArgs) == C.jb_ppo_fused_args_size()
+    names = [f[0] for f in FusedArgs._fields_]
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "jorldy_b200_fused.h")).read()
+    body = hdr[hdr.index("typedef struct jb_ppo_fused_args {") + len("typedef struct jb_ppo_fused_args {"):hdr.index("} jb_ppo_fused_args;")]
+    import re
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    decl = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        if not stmt or stmt.startswith("typedef"):
+            continue
+        for part in stmt.split(","):
+            m = re.search(r"\*?\s*([A-Za-z_][A-Za-z_0-9]*)\s*(\[\d+\])?\s*$", part.strip())
+            if m:
+                decl.append(m.group(1))
+    assert decl == names, (decl, names)
+
+
 def test_product_path_has_no_cpu_fallback():
     from jorldy_b200._lib import JbError
     from jorldy_b200.core import Agent
