@@ -237,13 +237,18 @@ def main():
         agent.learning_rate_decay(step_no[0])
         return res
 
+    trace_all = os.environ.get("JB_BENCH_TRACE", "0") == "1"
+
     def log(msg):
-        if rank == 0:
-            print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+        if rank == 0 or trace_all:
+            print(f"[bench {time.strftime('%H:%M:%S')} r{rank}] {msg}", file=sys.stderr, flush=True)
 
     log(f"world={world}: warm-up ({args.warmup} steps; first step captures the CUDA graphs)")
-    for _ in range(args.warmup):
+    for _w in range(args.warmup):
         res = one_step()
+        if trace_all:
+            torch.cuda.synchronize()
+            log(f"warm-up step {_w} done")
     log("timing")
     torch.cuda.synchronize()
     if world > 1:
@@ -398,4 +403,11 @@ def run_e2e(np, torch, Agent, Env, dev, rank=0, world=1, steps=2):
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as _e:      # every rank reports its own failure: torchrun's summary carries no traceback
+        if not isinstance(_e, SystemExit) or _e.code not in (0, None):
+            import traceback
+            sys.stderr.write(f"[bench rank {os.environ.get('RANK', 0)}] FAILED: {type(_e).__name__}: {_e}\n{traceback.format_exc()}\n")
+            sys.stderr.flush()
+        raise

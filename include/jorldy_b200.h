@@ -57,7 +57,7 @@ JB_API int jb_per_update(double* tree, int64_t capacity, const int64_t* tree_idx
                          void* stream);
 JB_API int jb_per_sample(const double* tree, int64_t capacity, int64_t counter, int B, double beta,
                          double uniform_sample_prob, const double* u_a, const double* u_b, uint64_t seed,
-                         uint64_t rng_ctr, const double* global_total, const int64_t* global_counter,
+                         uint64_t rng_ctr, const double* shard_prob, const int64_t* global_counter,
                          int64_t* out_idx, double* out_w, double* out_p, double* out_stats, int normalize,
                          void* stream);
 JB_API int jb_per_scale_weights(double* w, const double* wmax, int B, void* stream);

@@ -147,7 +147,7 @@ class PPO(BaseAgent):
 
     def _graph_for(self, st, B):
         """CUDA graph of GRAPH_CHUNK minibatch steps reading indices through the device cursor."""
-        key = (B, st["state"].data_ptr(), st["action"].data_ptr(), st["adv"].data_ptr())
+        key = (B,) + tuple(st[k].data_ptr() for k in ("state", "action", "adv", "ret", "value", "logp_old", "perm"))
         g = self._graphs.get(key)
         if g is not None:
             return g
@@ -160,7 +160,8 @@ class PPO(BaseAgent):
 
         # warm-up on a side stream (allocates workspaces), restoring every mutated buffer afterwards
         net, opt = self.network, self.optimizer
-        saved = [t.clone() for t in (net.flat, opt.exp_avg, opt.exp_avg_sq, opt._step_dev, self._acc, self._cursor)]
+        mutated = [net.flat, *opt.state_tensors(), self._acc, self._cursor]
+        saved = [t.clone() for t in mutated]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -168,7 +169,7 @@ class PPO(BaseAgent):
             self._minibatch_step(st, cur_idx, B)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        for dst, src in zip((net.flat, opt.exp_avg, opt.exp_avg_sq, opt._step_dev, self._acc, self._cursor), saved):
+        for dst, src in zip(mutated, saved):
             dst.copy_(src)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
@@ -183,6 +184,7 @@ class PPO(BaseAgent):
         NT = state.shape[0]
         T = self.n_step
         N = NT // T
+        assert N * T == NT, f"rollout of {NT} rows is not a multiple of n_step={T} (ppo.py:97 view(-1, n_step) would raise)"
         A = self.action_size
         dev = self.device
         s = stream_ptr()
@@ -265,7 +267,9 @@ class PPO(BaseAgent):
 
         acc = torch.cat([self._acc[:6], mean_ret.view(1), self._acc[7:8]]).cpu().numpy()     # ONE device->host read
         if acc[7] != 0.0:
-            raise RuntimeError("persistent PPO kernel: a peer GPU did not reach the gradient exchange (flag wait timed out)")
+            dbg = [ws["partials"][200:205].tolist() for ws in (r.ws for r in self._fused.values())]
+            raise RuntimeError("persistent PPO kernel: a peer GPU did not reach the gradient exchange (flag wait timed out); "
+                               f"[kind 1=grad-ready 2=done-reading, peer, step, seen, target] = {dbg}")
         cnt = max(acc[5], 1.0)
         return {
             "actor_loss": float(acc[0] / cnt),

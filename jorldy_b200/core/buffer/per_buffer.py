@@ -87,9 +87,10 @@ class PERBuffer(ReplayBuffer):
         stats f64 [4] = {sampled_p, mean_p, max raw weight, #uniform}).  u_a/u_b: injected uniforms.
 
         Sharded replay (Ape-X over G GPUs): when `self.shard_world > 1` this tree is one shard of
-        a G-way replay; each rank draws its B/G share locally, and the importance weights use the GLOBAL
-        sum of priorities / item count / max weight (per_buffer.py:88-94 evaluated over the union of the
-        shards) obtained with two tiny all-reduces (2 x f64 SUM, 1 x f64 MAX)."""
+        a G-way replay; each rank draws its B/G share locally.  Item i of shard r is therefore drawn with
+        probability (1/G) [(1-usp) p_i / total_r + usp / count_r] and the importance weight is
+        ((1/N_global) / that)^beta, normalised by the GLOBAL max weight (per_buffer.py:88-94 over the union of
+        the shards): two tiny all-reduces (2 x f64 SUM for N_global and the logged mean priority, 1 x f64 MAX)."""
         B = batch_size
         idx = torch.empty(B, dtype=torch.int64, device=self.device)
         w = torch.empty(B, dtype=torch.float64, device=self.device)
@@ -97,15 +98,16 @@ class PERBuffer(ReplayBuffer):
         stats = torch.empty(4, dtype=torch.float64, device=self.device)
         self._sample_ctr += 1
         sharded = getattr(self, "shard_world", 1) > 1
-        g_total = g_count = None
+        g_total = g_count = shard_p = None
         if sharded:
             import torch.distributed as dist
             tot = torch.stack([self._tree[0], torch.tensor(float(self.buffer_counter), dtype=torch.float64, device=self.device)])
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
             g_total = tot[0:1].contiguous()
             g_count = tot[1:2].to(torch.int64).contiguous()
+            shard_p = torch.full((1,), 1.0 / self.shard_world, dtype=torch.float64, device=self.device)
         C.jb_per_sample(ptr(self._tree), self.buffer_size, self.buffer_counter, B, float(beta),
-                        float(self.uniform_sample_prob), ptr(u_a), ptr(u_b), self.seed, self._sample_ctr, ptr(g_total),
+                        float(self.uniform_sample_prob), ptr(u_a), ptr(u_b), self.seed, self._sample_ctr, ptr(shard_p),
                         ptr(g_count), ptr(idx), ptr(w), ptr(p), ptr(stats), 0 if sharded else 1, stream_ptr())
         if sharded:
             import torch.distributed as dist

@@ -37,6 +37,10 @@ class _FlatOptimizer:
     def zero_grad(self, set_to_none=True):
         pass   # backward kernels overwrite the flat gradient buffer
 
+    def state_tensors(self):
+        """Every device tensor one step() mutates besides the parameters (CUDA-graph warm-ups save/restore these)."""
+        return [self._step_dev] + [getattr(self, n) for n in self._STATE]
+
     def _slot_views(self, flat):
         out = []
         for name, v in self.network.p.items():
@@ -46,6 +50,8 @@ class _FlatOptimizer:
 
 
 class Adam(_FlatOptimizer):
+    _STATE = ("exp_avg", "exp_avg_sq")
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, **kwargs):
         super().__init__(params, lr)
         self.betas, self.eps = betas, eps
@@ -86,6 +92,8 @@ class Adam(_FlatOptimizer):
 
 
 class RMSprop(_FlatOptimizer):
+    _STATE = ("square_avg", "grad_avg")
+
     def __init__(self, params, lr=1e-2, alpha=0.99, eps=1e-8, centered=False, **kwargs):
         super().__init__(params, lr)
         if not centered:

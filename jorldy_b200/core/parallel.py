@@ -22,28 +22,43 @@ def _try_p2p(agent, world_size):
     Falls back silently (agent.p2p = None -> CUDA graphs + NCCL) when symmetric memory is unavailable."""
     agent.p2p = None
     net = getattr(agent, "network", None)
+    # (these conditions are identical on every rank, so the early return is itself a collective decision)
     if net is None or not net.flat.is_cuda or dist.get_backend() != "nccl" or world_size > 8 or type(agent).__name__ != "PPO":
         return
+    # Step 1 — LOCAL probe only (no collective inside the try): can this rank allocate symmetric memory at all?
     ok, buf, hdl, ptrs, err = 1, None, None, None, None
+    symm = None
     try:
         import torch.distributed._symmetric_memory as symm
         n = net.num_flat + P2P_FLAG_WORDS
         buf = symm.empty(n, dtype=torch.float32, device=net.flat.device)
         buf.zero_()
         torch.cuda.synchronize()
+    except Exception as e:      # pragma: no cover - depends on the platform
+        ok, err = 0, e
+
+    def agree(ok_local):
+        flag = torch.tensor([ok_local], dtype=torch.int32, device=net.flat.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return int(flag.item()) == 1
+
+    def fallback():
+        import warnings
+        warnings.warn(f"in-kernel gradient exchange unavailable ({type(err).__name__ if err else 'peer'}: {err}); using NCCL all-reduce")
+
+    # Step 2 — agree BEFORE the collective rendezvous: a rank that failed locally must not leave the others blocked in it
+    if not agree(ok):
+        return fallback()
+    # Step 3 — the rendezvous itself is a collective every rank now enters; its outcome is agreed on again
+    try:
         hdl = symm.rendezvous(buf, dist.group.WORLD)
         ptrs = [int(p) for p in hdl.buffer_ptrs]
         if len(ptrs) != world_size or ptrs[dist.get_rank()] != buf.data_ptr():
             raise RuntimeError("unexpected symmetric-memory pointer table")
     except Exception as e:      # pragma: no cover - depends on the platform
         ok, err = 0, e
-    # the decision is collective: either every rank exchanges in-kernel or every rank uses NCCL
-    flag = torch.tensor([ok], dtype=torch.int32, device=net.flat.device)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if int(flag.item()) != 1:
-        import warnings
-        warnings.warn(f"in-kernel gradient exchange unavailable ({type(err).__name__ if err else 'peer'}: {err}); using NCCL all-reduce")
-        return
+    if not agree(ok):
+        return fallback()
     net.rebind_grad(buf)
     dist.barrier()
     agent.p2p = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "rank": dist.get_rank(), "world": world_size, "epoch": 0,

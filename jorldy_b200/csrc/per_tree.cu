@@ -38,7 +38,7 @@ __device__ __forceinline__ bool is_proper_ancestor(uint32_t a_plus1, uint32_t x_
 __global__ void __launch_bounds__(512) per_sample_kernel(const double* __restrict__ tree, int64_t first_leaf, int64_t counter,
                                   int B, double beta, double usp, const double* __restrict__ u_a,
                                   const double* __restrict__ u_b, uint64_t seed, uint64_t rng_ctr,
-                                  const double* __restrict__ global_total, const int64_t* __restrict__ global_counter,
+                                  const double* __restrict__ shard_prob, const int64_t* __restrict__ global_counter,
                                   int64_t* __restrict__ out_idx, double* __restrict__ out_w,
                                   double* __restrict__ out_p, double* __restrict__ out_stats, int normalize) {
   __shared__ int s_count;
@@ -58,8 +58,11 @@ __global__ void __launch_bounds__(512) per_sample_kernel(const double* __restric
   __syncthreads();
   const int K = s_count;
   const double total = tree[0];
-  const double tot_for_prob = global_total ? *global_total : total;
-  const double cnt_for_prob = (double)(global_counter ? *global_counter : counter);
+  // Sharded replay: this tree is one of G shards and receives a 1/G share of every batch, so item i of this shard is
+  // drawn with probability shard_prob * [(1-usp) p_i / total_local + usp / count_local]  (shard_prob = 1/G), while the
+  // uniform reference probability of the importance weight is 1 / N_global (per_buffer.py:88-93 over the union).
+  const double shard_p = shard_prob ? *shard_prob : 1.0;
+  const double cnt_global = (double)(global_counter ? *global_counter : counter);
 
   double wmax = 0.0, psum = 0.0;
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
@@ -83,10 +86,12 @@ __global__ void __launch_bounds__(512) per_sample_kernel(const double* __restric
     }
     const double p = tree[idx];
     // per_buffer.py:88-93
-    const double uniform_prob = 1.0 / cnt_for_prob;
-    const double prio_prob = p / tot_for_prob;
-    const double sample_prob = __dadd_rn(__dmul_rn(1.0 - usp, prio_prob), __dmul_rn(usp, uniform_prob));
-    const double w = pow(uniform_prob / sample_prob, beta);
+    const double uniform_prob = 1.0 / (double)counter;
+    const double prio_prob = p / total;
+    double sample_prob = __dadd_rn(__dmul_rn(1.0 - usp, prio_prob), __dmul_rn(usp, uniform_prob));
+    double ref_prob = uniform_prob;
+    if (shard_prob) { sample_prob = __dmul_rn(shard_p, sample_prob); ref_prob = 1.0 / cnt_global; }
+    const double w = pow(ref_prob / sample_prob, beta);
     out_idx[i] = idx; out_p[i] = p; out_w[i] = w;
     wmax = fmax(wmax, w); psum += p;
   }
@@ -251,19 +256,20 @@ JB_API int jb_per_update(double* tree, int64_t capacity, const int64_t* tree_idx
 
 // Draw B tree indices + importance weights.  u_a/u_b NULL -> Philox(seed, slot, rng_ctr).
 // out_stats[4] = {sampled_p, mean_p, max raw weight, #uniform slots}.
-// global_total/global_counter (device scalars, may be NULL) replace the local Σp / count in the
-// probability formula when the tree is one shard of a multi-GPU replay; with normalize=0 the raw
+// shard_prob/global_counter (device scalars, may be NULL): when the tree is one shard of a multi-GPU replay the
+// sampling probability is shard_prob x the local one and the weight's reference probability is
+// 1 / global_counter; with normalize=0 the raw
 // weights are returned so the caller can divide by the all-reduced max (jb_per_scale_weights).
 JB_API int jb_per_sample(const double* tree, int64_t capacity, int64_t counter, int B, double beta,
                          double uniform_sample_prob, const double* u_a, const double* u_b, uint64_t seed,
-                         uint64_t rng_ctr, const double* global_total, const int64_t* global_counter,
+                         uint64_t rng_ctr, const double* shard_prob, const int64_t* global_counter,
                          int64_t* out_idx, double* out_w, double* out_p, double* out_stats, int normalize,
                          void* stream) {
   if (!tree || capacity <= 0 || counter <= 0 || B <= 0 || !out_idx || !out_w || !out_p || !out_stats)
     return JB_ERR_INVALID;
   const int threads = B >= 512 ? 512 : ((B + 31) / 32) * 32;
   per_sample_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(tree, capacity - 1, counter, B, beta, uniform_sample_prob,
-                                                             u_a, u_b, seed, rng_ctr, global_total, global_counter,
+                                                             u_a, u_b, seed, rng_ctr, shard_prob, global_counter,
                                                              out_idx, out_w, out_p, out_stats, normalize);
   return jb_check_launch();
 }

@@ -525,7 +525,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       // peers read this rank's gradient of the PREVIOUS step over NVLink: they must be done before it is rewritten
       if (tid < a.world && tid != a.rank) {
         const unsigned int* f2 = reinterpret_cast<const unsigned int*>(a.peer[a.rank] + a.xflag_off) + 64 + tid;
-        if (!sys_flag_wait(f2, a.xbase + (unsigned int)s)) a.acc[7] = 1.f;
+        if (!sys_flag_wait(f2, a.xbase + (unsigned int)s)) {
+          a.acc[7] = 1.f;
+          if (cta == 0) { a.partials[200] = 2.f; a.partials[201] = (float)tid; a.partials[202] = (float)s; a.partials[203] = (float)*f2; a.partials[204] = (float)(a.xbase + (unsigned int)s); }
+        }
       }
       __syncthreads();
     }
@@ -851,7 +854,11 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
             __threadfence_system();
             sys_flag_set(reinterpret_cast<unsigned int*>(a.peer[tid] + a.xflag_off) + a.rank, target);
           }
-          if (!sys_flag_wait(reinterpret_cast<const unsigned int*>(a.peer[a.rank] + a.xflag_off) + tid, target)) a.acc[7] = 1.f;
+          const unsigned int* f1 = reinterpret_cast<const unsigned int*>(a.peer[a.rank] + a.xflag_off) + tid;
+          if (!sys_flag_wait(f1, target)) {
+            a.acc[7] = 1.f;
+            if (cta == 0) { a.partials[200] = 1.f; a.partials[201] = (float)tid; a.partials[202] = (float)s; a.partials[203] = (float)*f1; a.partials[204] = (float)target; }
+          }
         }
         __syncthreads();
 #pragma unroll
