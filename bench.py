@@ -52,7 +52,7 @@ def workload_config(world):
                         "(config.ppo.cartpole hyper-parameters, distributed_batch_size 256)",
             "n_envs_per_gpu": N_ENVS, "n_step": N_STEP, "batch_size_per_gpu": BATCH, "n_epoch": N_EPOCH,
             "hidden": HIDDEN, "parallelism": f"dp{world}",
-            "gradient_exchange": "none (1 GPU)" if world == 1 else "in-kernel peer-memory all-reduce per minibatch step (jorldy_b200/core/parallel.py)",
+            "gradient_exchange": "none (1 GPU)" if world == 1 else "in-kernel reduce-scatter + all-gather over NVLink peer memory, once per minibatch step (csrc/ppo_fused.cu, core/parallel.py)",
             "l2": "flushed between timed steps (256 MB fill, > 126 MB L2); every step re-collects its rollout"}
 
 

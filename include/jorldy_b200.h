@@ -49,6 +49,18 @@ JB_API int jb_gae(const float* reward, const float* done, const float* value, co
                   const float* last_value, int N, int T, float gamma, float lambda, int standardize,
                   float* adv, float* ret, void* stream);
 
+/* Synthetic continuous-control env with MuJoCo-task dimensions (replaces gym + mujoco_py behind
+ * jorldy/core/env/mujoco.py:25-58; BASELINE configs[4]: obs 11 / act 3).  s' = tanh(Ws s + Wa a) + 0.01 N(0,I),
+ * reward = -|s'|^2 / D, done ~ Bernoulli(p_done) or TimeLimit; obs f32 [n,D], action f32 [n,A]. */
+JB_API int
+jb_env_synth_reset(float* obs, int32_t* elapsed, int64_t* episode, float* score, uint64_t seed,
+                   uint64_t stream_base, int n, int D, void* stream);
+JB_API int
+jb_env_synth_step(float* obs, int32_t* elapsed, int64_t* episode, int64_t* tcount, float* score,
+                  const float* action, const float* Ws, const float* Wa, float* next_obs, float* reward,
+                  float* done, float* stats, int auto_reset, int max_steps, float p_done, uint64_t seed,
+                  uint64_t stream_base, int n, int D, int A, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * PER sum-tree — jorldy/core/buffer/per_buffer.py:19-101.  tree is f64[2*capacity-1].
  * ------------------------------------------------------------------------------------------- */

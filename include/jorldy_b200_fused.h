@@ -34,15 +34,29 @@ typedef struct jb_ppo_fused_args {
   long long *cursor;                 /* minibatch cursor (device) */
   const float *lr;                   /* learning rate (device scalar) */
   /* multi-GPU: gradient exchange through peer-mapped memory (world == 1: unused).  peer[r] = rank r's exchange
-   * buffer (the flat gradient followed by >= 256 uint32 flag words at float offset xflag_off); `grad` above is
-   * peer[rank].  Flags are monotonic: xbase = number of steps run by earlier launches. */
+   * buffer, laid out in floats as
+   *   [0, 4*P4)                     this rank's gradient (`grad` above is peer[rank])
+   *   [xgred_off, xgred_off+4*P4)   the AVERAGED gradient: slice q of it is written by rank q (reduce-scatter by the
+   *                                 slice owner, then the owner stores its averaged slice into every rank)
+   *   [xflag_off, +JB_X_WORDS)      32-bit words: JB_X_F1 "gradient of step s complete" per source rank,
+   *                                 JB_X_MSG {sum (v-ret)^2, sum (v_clip-ret)^2, tag, -} per source rank (the two
+   *                                 critic means of ppo.py:151-154 are global), JB_X_PTAB {||slice chunk||^2, tag}
+   *                                 per (owner rank, owner CTA): a chunk's tag says "chunk stored in your copy".
+   * Tags are monotonic: xbase = number of steps run by earlier launches. */
   float *peer[8];
   int world, rank;
   unsigned int xbase;
-  int xflag_off;
+  int xflag_off, xgred_off;
   int nh[3];                         /* outputs per head */
   int B, D, H, A, nout, continuous, n_steps;
   float eps_clip, vf_coef, ent_coef, beta1, beta2, adam_eps, max_norm;
 } jb_ppo_fused_args;
+
+/* word offsets inside the flag region of the exchange buffer */
+#define JB_X_F1 0
+#define JB_X_MSG 64
+#define JB_X_PTAB 128
+#define JB_X_MAX_CTAS 256
+#define JB_X_WORDS (JB_X_PTAB + 8 * JB_X_MAX_CTAS * 2)
 
 #endif

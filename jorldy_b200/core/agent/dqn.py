@@ -318,18 +318,19 @@ class Noisy(DQN):
     def _forward_q(self, net, x, tag, is_train=True, noise=None):
         return net.forward(x, is_train, tag=tag, noise=noise)
 
-    def _q_values(self, state, training, tag="act."):
+    def _q_values(self, state, training, tag="act.", noise=None):
         M = state.shape[0]
         q = self.network._buf(tag + "q", (M, self.action_size))
-        self.network.forward_rows(state, q, is_train=training)
+        self.network.forward_rows(state, q, is_train=training, noise=noise)
         return q
 
     def act_device(self, state, training=True, noise=None):
+        """noise: injected NoisyNet draws [(eps_i, eps_j)] x 2 for this forward (parity tests)."""
         M = state.shape[0]
         if training and self.memory.size < max(self.batch_size, self.start_train_step):
             action = torch.randint(0, self.action_size, (M,), device=self.device)      # noisy.py:71-72
             return action, None
-        q = self._q_values(state, training)
+        q = self._q_values(state, training, noise=noise)
         return torch.argmax(q, -1), None
 
     def learn(self):
@@ -446,11 +447,13 @@ class Rainbow(PER, _Distributional):
         return net.forward(x, True, tag=tag, noise=noise)
 
     def act_device(self, state, training=True, noise=None):
+        """One noisy forward for all rows (the reference's act() with a batch of N states draws its noise once per
+        call, rainbow.py:149).  noise: injected draws [(eps_i, eps_j)] x 4 in call order a1, v1, a2, v2."""
         M = state.shape[0]
         if training and self.memory.size < max(self.batch_size, self.start_train_step):
             return torch.randint(0, self.action_size, (M,), device=self.device), None       # rainbow.py:143-147
         logits = self.network._buf("act.logits", (M, self.action_size, self.num_support))
-        self.network.forward_rows(state, logits, is_train=training)
+        self.network.forward_rows(state, logits, is_train=training, noise=noise)
         return torch.argmax(self._expected_q(logits, M), -1), None
 
     def learn(self):

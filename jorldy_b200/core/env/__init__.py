@@ -3,10 +3,15 @@ from collections import OrderedDict
 
 from .classic import Cartpole, Pendulum, MountainCar
 from .frames import SyntheticAtari, _ACTIONS
+from .synth import SyntheticControl, _DIMS
 
 env_dict = OrderedDict(cartpole=Cartpole, mountain_car=MountainCar, pendulum=Pendulum, synthetic_atari=SyntheticAtari)
 for _game in _ACTIONS:            # atari.py registers one class per game (Breakout, Pong, ...)
     env_dict[_game] = (lambda g: (lambda **kw: SyntheticAtari(name=g, **kw)))(_game)
+
+
+for _task in _DIMS:              # mujoco.py registers one class per task (Hopper, HalfCheetah, ...)
+    env_dict[_task] = (lambda g: (lambda **kw: SyntheticControl(name=g, **kw)))(_task)
 
 
 def register(name, cls):

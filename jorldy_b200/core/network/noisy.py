@@ -92,11 +92,11 @@ class Noisy(FlatNetwork, _NoisyMixin):
         self._noisy_fwd(h, tag, "2", 2, H, A, out, False, is_train, n2)
         return out
 
-    def forward_rows(self, x, out, is_train=True):
+    def forward_rows(self, x, out, is_train=True, noise=None):
         M = x.shape[0]
         for s in range(0, M, self.head.max_rows):
             e = min(M, s + self.head.max_rows)
-            self.forward(x[s:e], is_train, None, e - s, out[s:e], tag=f"inf{e - s}.", save=False)
+            self.forward(x[s:e], is_train, None, e - s, out[s:e], tag=f"inf{e - s}.", save=False, noise=noise)
         return out
 
     def backward(self, dq, M, tag="t."):
@@ -150,12 +150,12 @@ class Rainbow(FlatNetwork, _NoisyMixin):
         C.jb_dueling_fwd(ptr(a), ptr(v), M, A, K, ptr(out), stream_ptr())
         return out
 
-    def forward_rows(self, x, out, is_train=True):
-        """Chunked inference (act() over many env rows); out [M, A, K]."""
+    def forward_rows(self, x, out, is_train=True, noise=None):
+        """Chunked inference (act() over many env rows); out [M, A, K].  noise: injected draws (parity tests)."""
         M = x.shape[0]
         for s in range(0, M, self.head.max_rows):
             e = min(M, s + self.head.max_rows)
-            self.forward(x[s:e], is_train, None, e - s, out[s:e], tag=f"inf{e - s}.", save=False)
+            self.forward(x[s:e], is_train, None, e - s, out[s:e], tag=f"inf{e - s}.", save=False, noise=noise)
         return out
 
     def backward(self, dlogits, M, tag="t."):

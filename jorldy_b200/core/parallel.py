@@ -12,13 +12,14 @@ import torch
 import torch.distributed as dist
 
 
-P2P_FLAG_WORDS = 256     # uint32 flag words appended to the exchange buffer (zeroed before the rendezvous)
+P2P_FLAG_WORDS = 128 + 8 * 256 * 2     # JB_X_WORDS of include/jorldy_b200_fused.h (zeroed before the rendezvous)
 
 
 def _try_p2p(agent, world_size):
     """Peer-mapped gradient exchange buffer for the persistent PPO kernel (csrc/ppo_fused.cu): every rank's flat
-    gradient lives in a symmetric-memory allocation whose peer pointers the kernel reads over NVLink, so the
-    all-reduce happens INSIDE the kernel (peer loads + flag barrier) instead of 6144 NCCL calls per learn().
+    gradient lives in a symmetric-memory allocation whose peer pointers the kernel reads and writes over NVLink, so
+    the gradient average (reduce-scatter by slice owners + all-gather by stores, flags in the same buffer) happens
+    INSIDE the kernel instead of 6144 NCCL calls per learn().
     Falls back silently (agent.p2p = None -> CUDA graphs + NCCL) when symmetric memory is unavailable."""
     agent.p2p = None
     net = getattr(agent, "network", None)
@@ -30,7 +31,9 @@ def _try_p2p(agent, world_size):
     symm = None
     try:
         import torch.distributed._symmetric_memory as symm
-        n = net.num_flat + P2P_FLAG_WORDS
+        if net.num_flat % 4:
+            raise RuntimeError("flat parameter buffer is not a whole number of float4")
+        n = 2 * net.num_flat + P2P_FLAG_WORDS     # gradient | averaged gradient | flag words
         buf = symm.empty(n, dtype=torch.float32, device=net.flat.device)
         buf.zero_()
         torch.cuda.synchronize()
@@ -62,7 +65,7 @@ def _try_p2p(agent, world_size):
     net.rebind_grad(buf)
     dist.barrier()
     agent.p2p = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "rank": dist.get_rank(), "world": world_size, "epoch": 0,
-                 "flag_off": net.num_flat}
+                 "gred_off": net.num_flat, "flag_off": 2 * net.num_flat}
 
 
 def attach(agent, world_size, average_with="avg"):

@@ -34,13 +34,22 @@
 // (L2), and the barrier's gpu-scope release/acquire orders the phases.
 //
 // Multi-GPU (args.world > 1): every rank's flat gradient lives in a peer-mapped exchange buffer (args.peer[r],
-// torch symmetric memory).  After the backward phase's barrier the kernel publishes a "gradient complete" flag to all
-// peers, waits for theirs, and every CTA reads ITS Adam slice of every rank's gradient over NVLink (rank order =>
-// identical bits everywhere), averages, and the clip norm is taken of the averaged gradient (one more grid barrier);
-// a second flag tells the peers their gradients may be overwritten.  No NCCL call between backward and Adam.
+// torch symmetric memory) and the gradient average is a reduce-scatter + all-gather done by the kernel itself:
+//   * after the backward phase's barrier CTA 0 tells every peer "gradient of step s complete" (one flag word each);
+//   * rank q OWNS slice q of the flat gradient, CTA c of rank q chunk c of that slice: it reads the chunk from all
+//     ranks (NVLink loads, all in flight), sums in rank order, scales by 1/world, stores the averaged chunk into
+//     EVERY rank's "averaged gradient" buffer (NVLink stores) and then publishes {||chunk||^2, tag} to every rank;
+//   * every CTA waits for the tags of all world x grid chunks, folds the partial norms in a fixed order (identical
+//     bits on all ranks) and applies clip + Adam to its slice of the local copy of the averaged gradient.
+//   Per step and rank this moves 2 (world-1)/world of the gradient over NVLink (the first version read every
+//   rank's full gradient: world-1 times) and needs no grid barrier beyond the single-GPU three.
+//   * the two scalar means of critic_loss = max(mean, mean) (ppo.py:151-154) are GLOBAL: each rank sends its two row
+//     sums to the peers during the row phase (16-byte message + tag); receiving step s's message from a peer also
+//     proves that the peer has finished reading this rank's gradient of step s-1, so it may be overwritten.
+// No NCCL call between backward and Adam.
 //
 // Constraints (else the host uses the multi-launch path): B % 32 == 0, B <= 512, H % 32 == 0, H <= 512,
-// D <= 16, nout <= 8; multi-GPU additionally: <= 8 ranks, <= 8 K parameters per CTA slice (1.2 M parameters).
+// D <= 16, nout <= 8; multi-GPU additionally: <= 8 ranks.
 #include <cstdlib>
 #include "common.cuh"
 #include "ppo_rowmath.cuh"
@@ -109,17 +118,49 @@ struct Stager {
   }
 };
 
-// ---- cross-GPU flag wait (multi-GPU gradient exchange): bounded, so that a dead peer cannot hang this GPU
-__device__ __forceinline__ bool sys_flag_wait(const unsigned int* flag, unsigned int target) {
-  for (unsigned int it = 0; it < (1u << 25); ++it) {   // ~20-30 s of polling
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
-    if ((int)(v - target) >= 0) return true;
+// ---- cross-GPU flag wait (multi-GPU gradient exchange): bounded by WALL-CLOCK time (a peer may legitimately be
+// seconds late: it is another process with its own host-side launch sequence), and once one wait has given up every
+// later wait returns at once (`abort_flag`, a word of this GPU's barrier block), so that a dead peer costs one timeout
+// per launch instead of one per step; the host then raises (ppo.py checks acc[7]).
+constexpr unsigned long long X_TIMEOUT_NS = 60ull * 1000ull * 1000ull * 1000ull;
+constexpr int CTR_ABORT = 63;                           // a.barrier[CTR_ABORT] != 0: an exchange wait timed out
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool sys_flag_wait(const unsigned int* flag, unsigned int target, unsigned int* abort_flag) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
+  if ((int)(v - target) >= 0) return true;
+  const unsigned long long t0 = global_ns();
+  for (;;) {
+    for (int it = 0; it < 32; ++it) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
+      if ((int)(v - target) >= 0) return true;
+    }
+    unsigned int ab;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(ab) : "l"(abort_flag) : "memory");
+    if (ab) return false;
+    if (global_ns() - t0 > X_TIMEOUT_NS) {
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(abort_flag), "r"(1u) : "memory");
+      return false;
+    }
   }
-  return false;
 }
 __device__ __forceinline__ void sys_flag_set(unsigned int* flag, unsigned int value) {
   asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(flag), "r"(value) : "memory");
+}
+__device__ __forceinline__ void st_sys4(float* p, float4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float ld_sys1(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys1(float* p, float v) {
+  asm volatile("st.relaxed.sys.global.f32 [%0], %1;\n" ::"l"(p), "f"(v) : "memory");
 }
 __device__ __forceinline__ float4 ld_sys4(const float* p) {
   float4 v;
@@ -521,17 +562,6 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
     TR(6);
 
     // =========================== P3: row phase + backward jobs =========================================
-    if (a.world > 1) {
-      // peers read this rank's gradient of the PREVIOUS step over NVLink: they must be done before it is rewritten
-      if (tid < a.world && tid != a.rank) {
-        const unsigned int* f2 = reinterpret_cast<const unsigned int*>(a.peer[a.rank] + a.xflag_off) + 64 + tid;
-        if (!sys_flag_wait(f2, a.xbase + (unsigned int)s)) {
-          a.acc[7] = 1.f;
-          if (cta == 0) { a.partials[200] = 2.f; a.partials[201] = (float)tid; a.partials[202] = (float)s; a.partials[203] = (float)*f2; a.partials[204] = (float)(a.xbase + (unsigned int)s); }
-        }
-      }
-      __syncthreads();
-    }
     int pre_job = -1;                              // job whose first panels are already in flight
     if (cta < nJ3 && (cta < nJB || prefetchable(cta))) { issue_stage(cta); pre_job = cta; }
     // row ids of the NEXT step's first P1 tile: the load is in flight during the whole phase
@@ -592,7 +622,35 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       float t1 = 0.f, t2 = 0.f;
 #pragma unroll
       for (int w = 0; w < NT / 32; ++w) { t1 += scr[w * 8]; t2 += scr[w * 8 + 1]; }
-      c1 = t1 * invB; c2 = t2 * invB;
+      float invBW = invB;
+      if (a.world > 1) {
+        // the two means of critic_loss = max(mean, mean) run over the GLOBAL minibatch (all ranks' rows): exchange the
+        // row sums.  A peer's message for step s also says "I have finished step s-1", i.e. it no longer reads this
+        // rank's gradient buffer, which the backward jobs below overwrite.
+        const unsigned int target = a.xbase + (unsigned int)s + 1u;
+        if (tid < a.world && tid != a.rank) {
+          if (cta == 0) {
+            float* dst = a.peer[tid] + a.xflag_off + JB_X_MSG + 4 * a.rank;
+            st_sys1(dst, t1); st_sys1(dst + 1, t2);
+            sys_flag_set(reinterpret_cast<unsigned int*>(dst) + 2, target);      // release: orders the two values
+          }
+          const unsigned int* tag = reinterpret_cast<const unsigned int*>(a.peer[a.rank] + a.xflag_off + JB_X_MSG + 4 * tid) + 2;
+          if (!sys_flag_wait(tag, target, a.barrier + CTR_ABORT)) {
+            a.acc[7] = 1.f;
+            if (cta == 0) { a.partials[200] = 3.f; a.partials[201] = (float)tid; a.partials[202] = (float)s; a.partials[203] = (float)*tag; a.partials[204] = (float)target; }
+          }
+        }
+        __syncthreads();
+        float g1 = 0.f, g2 = 0.f;
+        for (int r = 0; r < a.world; ++r) {                  // rank order: identical bits on every rank
+          const float* m = a.peer[a.rank] + a.xflag_off + JB_X_MSG + 4 * r;
+          g1 += r == a.rank ? t1 : ld_sys1(m);
+          g2 += r == a.rank ? t2 : ld_sys1(m + 1);
+        }
+        t1 = g1; t2 = g2;
+        invBW = invB / (float)a.world;
+      }
+      c1 = t1 * invBW; c2 = t2 * invBW;
       float w1, w2;
       jbppo::critic_weights(c1, c2, w1, w2);
       for (int b = tid; b < B; b += NT) dsm[b * MAXO + npol] = w1 * dsm[b * MAXO + npol] + w2 * dvs[b];
@@ -846,49 +904,67 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           if (i < hi) gg[it] = __ldcg(g4 + i);
         }
       } else {
-        // ---- gradient all-reduce over peer memory (NVLink): flag barrier, then every CTA averages ITS slice of all
-        // ranks' gradients in rank order (identical bits everywhere), then the norm of the averaged gradient
+        // ---- gradient average over peer memory (NVLink): reduce-scatter by the slice owners + all-gather by stores
         const unsigned int target = a.xbase + (unsigned int)s + 1u;
+        unsigned int* myx = reinterpret_cast<unsigned int*>(a.peer[a.rank] + a.xflag_off);
         if (tid < a.world && tid != a.rank) {
           if (cta == 0) {                                            // this rank's gradient is complete (barrier above)
             __threadfence_system();
-            sys_flag_set(reinterpret_cast<unsigned int*>(a.peer[tid] + a.xflag_off) + a.rank, target);
+            sys_flag_set(reinterpret_cast<unsigned int*>(a.peer[tid] + a.xflag_off) + JB_X_F1 + a.rank, target);
           }
-          const unsigned int* f1 = reinterpret_cast<const unsigned int*>(a.peer[a.rank] + a.xflag_off) + tid;
-          if (!sys_flag_wait(f1, target)) {
+          const unsigned int* f1 = myx + JB_X_F1 + tid;
+          if (!sys_flag_wait(f1, target, a.barrier + CTR_ABORT)) {
             a.acc[7] = 1.f;
             if (cta == 0) { a.partials[200] = 1.f; a.partials[201] = (float)tid; a.partials[202] = (float)s; a.partials[203] = (float)*f1; a.partials[204] = (float)target; }
           }
         }
         __syncthreads();
+        {
+          // this CTA owns chunk `cta` of slice `rank`
+          const long long q4 = (a.P4 + a.world - 1) / a.world, c4 = (q4 + nctas - 1) / nctas;
+          const long long sl_hi = min(a.P4, (long long)(a.rank + 1) * q4);
+          const long long ch_lo = (long long)a.rank * q4 + (long long)cta * c4, ch_hi = min(sl_hi, ch_lo + c4);
+          const float inv_world = 1.f / (float)a.world;
+          float sqa = 0.f;
+          for (long long i = ch_lo + tid; i < ch_hi; i += NT) {
+            float4 t[8];
 #pragma unroll
-        for (int it = 0; it < ADAM_IT; ++it) gg[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-        for (int r = 0; r < a.world; ++r) {
-          const float* src = a.peer[r];
-          float4 t[ADAM_IT];
+            for (int r = 0; r < 8; ++r)                              // all ranks' loads in flight together
+              if (r < a.world) t[r] = r == a.rank ? __ldcg(g4 + i) : ld_sys4(a.peer[r] + 4 * i);
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int it = 0; it < ADAM_IT; ++it) {
-            const long long i = lo + tid + it * NT;
-            t[it] = i < hi ? ld_sys4(src + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < 8; ++r)                              // rank order: the same bits whoever owns the chunk
+              if (r < a.world) { sum.x += t[r].x; sum.y += t[r].y; sum.z += t[r].z; sum.w += t[r].w; }
+            sum.x *= inv_world; sum.y *= inv_world; sum.z *= inv_world; sum.w *= inv_world;
+            sqa = fmaf(sum.x, sum.x, sqa); sqa = fmaf(sum.y, sum.y, sqa); sqa = fmaf(sum.z, sum.z, sqa); sqa = fmaf(sum.w, sum.w, sqa);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              if (r < a.world) st_sys4(a.peer[r] + a.xgred_off + 4 * i, sum);
           }
-#pragma unroll
-          for (int it = 0; it < ADAM_IT; ++it) { gg[it].x += t[it].x; gg[it].y += t[it].y; gg[it].z += t[it].z; gg[it].w += t[it].w; }
+          const float tot = block_sum(sqa, scr + 64);                // (its barriers order every thread's stores before the tags)
+          if (tid < a.world) {
+            __threadfence_system();
+            float* dst = a.peer[tid] + a.xflag_off + JB_X_PTAB + 2 * (a.rank * JB_X_MAX_CTAS + cta);
+            st_sys1(dst, tot);
+            sys_flag_set(reinterpret_cast<unsigned int*>(dst) + 1, target);
+          }
         }
-        const float inv_world = 1.f / (float)a.world;
-        float sqa = 0.f;
+        // every chunk of every owner has landed in this rank's copy of the averaged gradient?
+        for (int e = tid; e < a.world * (int)nctas; e += NT) {
+          const int r = e / (int)nctas, c = e - r * (int)nctas;
+          const unsigned int* tag = myx + JB_X_PTAB + 2 * (r * JB_X_MAX_CTAS + c) + 1;
+          if (!sys_flag_wait(tag, target, a.barrier + CTR_ABORT)) {
+            a.acc[7] = 1.f;
+            if (cta == 0) { a.partials[200] = 2.f; a.partials[201] = (float)r; a.partials[202] = (float)s; a.partials[203] = (float)c; a.partials[204] = (float)target; }
+          }
+        }
+        __syncthreads();
+        const float4* gr4 = reinterpret_cast<const float4*>(a.peer[a.rank] + a.xgred_off);
 #pragma unroll
         for (int it = 0; it < ADAM_IT; ++it) {
-          gg[it].x *= inv_world; gg[it].y *= inv_world; gg[it].z *= inv_world; gg[it].w *= inv_world;
-          sqa = fmaf(gg[it].x, gg[it].x, sqa); sqa = fmaf(gg[it].y, gg[it].y, sqa);
-          sqa = fmaf(gg[it].z, gg[it].z, sqa); sqa = fmaf(gg[it].w, gg[it].w, sqa);
+          const long long i = lo + tid + it * NT;
+          if (i < hi) gg[it] = __ldcg(gr4 + i);
         }
-        const float tot = block_sum(sqa, scr + 64);
-        if (tid == 0) a.partials[cta] = tot;
-        grid_bar(a.barrier, epoch, nctas);
-        // every CTA of this rank has read the peers' gradients of this step: they may overwrite them
-        if (cta == 0 && tid < a.world && tid != a.rank)
-          sys_flag_set(reinterpret_cast<unsigned int*>(a.peer[tid] + a.xflag_off) + 64 + a.rank, target);
       }
       // next step's state rows (sidx was published before the barrier)
       float xv[2] = {0.f, 0.f};
@@ -897,7 +973,15 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         for (int q = 0; q < 2; ++q) { const int e = tid + q * NT, r = e >> 4, i = e & 15; if (i < D) xv[q] = a.state[(size_t)sidx[r] * D + i]; }
       }
       // ||g||: one coalesced read of the partials per CTA, then every warp folds them in the same fixed order
-      if (tid < (int)nctas) dvs[tid] = ldcg(a.partials + tid);
+      if (tid < (int)nctas) {
+        if (a.world == 1) dvs[tid] = ldcg(a.partials + tid);
+        else {                                       // chunk norms of all owners, owner-rank order
+          const float* pt = a.peer[a.rank] + a.xflag_off + JB_X_PTAB;
+          float t = 0.f;
+          for (int r = 0; r < a.world; ++r) t += ld_sys1(pt + 2 * (r * JB_X_MAX_CTAS + tid));
+          dvs[tid] = t;
+        }
+      }
       if (s + 1 < a.n_steps) gather_rows();        // next step's rollout values (row ids were loaded in P3)
       __syncthreads();
       float pv[NT / 32];
@@ -939,7 +1023,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       }
       for (long long i = lo + tid + (long long)ADAM_IT * NT; i < hi; i += NT) {   // slices beyond 8 K floats per CTA
         float4 p_ = __ldcg(p4 + i), m_ = __ldcg(m4 + i), v_ = __ldcg(v4 + i);
-        const float4 g_ = __ldcg(g4 + i);
+        const float4 g_ = __ldcg((a.world > 1 ? reinterpret_cast<const float4*>(a.peer[a.rank] + a.xgred_off) : g4) + i);
         upd(p_.x, g_.x, m_.x, v_.x); upd(p_.y, g_.y, m_.y, v_.y); upd(p_.z, g_.z, m_.z, v_.z); upd(p_.w, g_.w, m_.w, v_.w);
         p4[i] = p_; m4[i] = m_; v4[i] = v_;
         shadow(i, p_);
@@ -995,8 +1079,10 @@ JB_API int jb_ppo_fused_run(const void* host_args, void* stream) {
   if (ctas <= 0) return JB_ERR_INVALID;
   if (ctas > NT) ctas = NT;
   if (a.world < 1 || a.world > 8 || a.rank < 0 || a.rank >= a.world) return JB_ERR_INVALID;
-  if (a.world > 1) {   // the exchange keeps a CTA's gradient slice in registers; grad must be this rank's exchange buffer
-    if (a.P4 > (long long)ctas * ADAM_IT * NT || a.peer[a.rank] != a.grad || a.xflag_off < a.P4 * 4) return JB_ERR_INVALID;
+  if (a.world > 1) {   // grad must be this rank's exchange buffer: gradient | averaged gradient | flag words
+    if (a.peer[a.rank] != a.grad || a.xgred_off < a.P4 * 4 || a.xflag_off < a.xgred_off + a.P4 * 4 || (a.xgred_off & 3) ||
+        (a.xflag_off & 3) || ctas > JB_X_MAX_CTAS)
+      return JB_ERR_INVALID;
     for (int r = 0; r < a.world; ++r) if (!a.peer[r]) return JB_ERR_INVALID;
   }
   cudaStream_t s = (cudaStream_t)stream;

@@ -180,3 +180,72 @@ class MountainCarBatch:
         if self.auto_reset and done.any():
             self._draw(done)
         return next_obs, reward, done
+
+
+class SyntheticControlBatch:
+    """numpy restatement of csrc/env_synth.cu (synthetic generator with Hopper-v3 DIMENSIONS standing in for
+    jorldy/core/env/mujoco.py: our own definition, not a restatement of MuJoCo — "parity" here means the CUDA kernel
+    computes what its header says).  float32 arithmetic in the kernel's operation order; Philox counters:
+    16 t + k for the 4 normals of dims 4k..4k+3, 16 t + 15 for the done draw, 2^40 + 16 episode + k for reset."""
+
+    def __init__(self, n, D=11, A=3, seed=0, stream_base=0, auto_reset=True, p_done=1e-3, max_steps=1000, Ws=None, Wa=None):
+        self.n, self.D, self.A, self.seed, self.stream_base, self.auto_reset = n, D, A, seed, stream_base, auto_reset
+        self.p_done, self.max_steps = np.float32(p_done), max_steps
+        self.Ws, self.Wa = np.asarray(Ws, np.float32), np.asarray(Wa, np.float32)
+        self.ids = np.arange(n, dtype=np.uint64)
+        self.obs = np.zeros((n, D), np.float32)
+        self.elapsed = np.zeros(n, np.int32)
+        self.episode = np.zeros(n, np.int64)
+        self.tcount = np.zeros(n, np.int64)
+
+    def _reset_draw(self, mask):
+        ids, ep = self.ids[mask], self.episode[mask].astype(np.uint64)
+        cols = []
+        for k in range((self.D + 3) // 4):
+            w = philox.philox4x32(self.seed, np.uint64(self.stream_base) + ids, (np.uint64(1) << np.uint64(40)) + np.uint64(16) * ep + np.uint64(k))
+            cols += [np.float32(-0.05) + np.float32(0.1) * philox.u01_float(x) for x in w]
+        self.obs[mask] = np.stack(cols[:self.D], axis=1).astype(np.float32)
+        self.episode[mask] += 1
+        self.elapsed[mask] = 0
+
+    def reset(self):
+        self._reset_draw(np.ones(self.n, bool))
+        return self.obs.copy()
+
+    def step(self, action):
+        a = np.asarray(action, np.float32).reshape(self.n, self.A)
+        s, t = self.obs, self.tcount.astype(np.uint64)
+        stream = np.uint64(self.stream_base) + self.ids
+        sn = np.zeros_like(s)
+        sq = np.zeros(self.n, np.float32)
+        for k0 in range(0, self.D, 4):
+            w = philox.philox4x32(self.seed, stream, np.uint64(16) * t + np.uint64(k0 >> 2))
+            nrm = []
+            for h in range(2):
+                u1 = ((w[2 * h] >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * np.float32(1.0 / 16777216.0)
+                u2 = philox.u01_float(w[2 * h + 1])
+                rad = np.sqrt(np.float32(-2.0) * np.log(u1)).astype(np.float32)
+                ang = (np.float32(2.0) * u2).astype(np.float64) * np.pi
+                nrm += [(rad * np.cos(ang).astype(np.float32)).astype(np.float32), (rad * np.sin(ang).astype(np.float32)).astype(np.float32)]
+            for q in range(4):
+                k = k0 + q
+                if k >= self.D:
+                    break
+                z = np.zeros(self.n, np.float32)
+                for j in range(self.D):
+                    z = (z + self.Ws[k, j] * s[:, j]).astype(np.float32)
+                for j in range(self.A):
+                    z = (z + self.Wa[k, j] * a[:, j]).astype(np.float32)
+                v = (np.tanh(z).astype(np.float32) + np.float32(0.01) * nrm[q]).astype(np.float32)
+                sn[:, k] = v
+                sq = (sq + v * v).astype(np.float32)
+        reward = (-sq / np.float32(self.D)).astype(np.float32)
+        wd = philox.philox4x32(self.seed, stream, np.uint64(16) * t + np.uint64(15))
+        self.tcount += 1
+        self.elapsed += 1
+        done = (philox.u01_float(wd[0]) < self.p_done) | (self.elapsed >= self.max_steps)
+        next_obs = sn.copy()
+        self.obs = sn
+        if self.auto_reset and done.any():
+            self._reset_draw(done)
+        return next_obs, reward, done

@@ -123,3 +123,32 @@ def test_mountain_car_matches_oracle():
         np.testing.assert_allclose(ns, rns, rtol=0, atol=1e-7)
         assert np.array_equal(d.reshape(-1), rd) and np.all(r == -1.0)
         np.testing.assert_allclose(env.phys.cpu().numpy(), ref.phys, rtol=0, atol=1e-14)
+
+
+def test_synthetic_control_matches_oracle():
+    """Hopper-dimension synthetic generator (csrc/env_synth.cu) vs its numpy restatement: reset draws and done flags
+    bit-exact (Philox), observations / rewards within 2e-6 (tanhf, Box-Muller logf / cospif differ by an ulp)."""
+    from jorldy_b200.core import Env
+    from jorldy_b200.core.env.synth import synth_weights
+    from oracle.classic_control import SyntheticControlBatch
+    n, D, A = 512, 11, 3
+    env = Env("hopper", num_envs=n, seed=7, id=2, device="cuda", p_done=0.05, max_steps=20)
+    assert env.state_size == 11 and env.action_size == 3 and env.action_type == "continuous"
+    Ws, Wa = synth_weights(D, A, 0)
+    ref = SyntheticControlBatch(n, D, A, seed=7, stream_base=2 << 32, p_done=0.05, max_steps=20, Ws=Ws, Wa=Wa)
+    o = env.reset_device().cpu().numpy()
+    np.testing.assert_array_equal(o, ref.reset())
+    rs = np.random.RandomState(0)
+    n_done = 0
+    for t in range(40):
+        a = np.tanh(rs.standard_normal((n, A))).astype(np.float32)
+        nobs, r, d = env.step_device(torch.from_numpy(a).cuda())
+        rn, rr, rd = ref.step(a)
+        np.testing.assert_array_equal(d.cpu().numpy() > 0.5, rd, err_msg=f"done step {t}")
+        np.testing.assert_allclose(nobs.cpu().numpy(), rn, rtol=0, atol=2e-6, err_msg=f"next_obs step {t}")
+        np.testing.assert_allclose(r.cpu().numpy(), rr, rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(env.obs.cpu().numpy(), ref.obs, rtol=0, atol=2e-6)     # post auto-reset observation
+        ref.obs = env.obs.cpu().numpy().copy()          # re-synchronise so ulp differences do not accumulate
+        n_done += int(rd.sum())
+    assert n_done > 100                                  # Bernoulli and TimeLimit terminations both exercised
+    assert int(env.elapsed.max().item()) < 20
