@@ -26,11 +26,13 @@ def _opt(params, optim):
     raise ValueError(name)
 
 
-def td_learn(params, target_params, batch, hp, optim):
+def td_learn(params, target_params, batch, hp, optim, opt_state=None):
     """hp: net ("dqn"|"dueling"|"noisy"), gamma, n_step, double (bool), loss ("huber"|"wmse"), order
     ("dqn"|"double"|"nstep"), alpha, clip (float|None), noise (None | [noise_s, noise_next, noise_target])."""
     p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     opt = _opt(list(p.values()), optim)
+    if opt_state is not None:             # multi-step CPU baselines carry Adam / RMSprop state across learn() calls
+        opt.load_state_dict(opt_state)
     state, action, reward = batch["state"], batch["action"], batch["reward"]
     next_state, done = batch["next_state"], batch["done"]
     A = hp["action_size"]
@@ -70,12 +72,13 @@ def td_learn(params, target_params, batch, hp, optim):
         loss = (w * (td_error ** 2)).mean()
     opt.zero_grad(set_to_none=True)
     loss.backward()
-    out["grads"] = {k: v.grad.clone() for k, v in p.items()}
+    out["grads"] = {k: (v.grad.clone() if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
     if hp.get("clip"):
         torch.nn.utils.clip_grad_norm_(list(p.values()), hp["clip"])
     opt.step()
     out["params"] = {k: v.detach().clone() for k, v in p.items()}
     out["loss"], out["max_Q"] = loss.item(), max_Q
+    out["opt_state"] = opt.state_dict()
     return out
 
 
@@ -88,10 +91,12 @@ def _logits2Q(logits, A, K, z, subtract_max):
     return p, q
 
 
-def dist_learn(params, target_params, batch, hp, optim):
+def dist_learn(params, target_params, batch, hp, optim, opt_state=None):
     """hp: variant ("c51"|"rainbow"), action_size, num_support, v_min, v_max, gamma, n_step, alpha, noise."""
     p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     opt = _opt(list(p.values()), optim)
+    if opt_state is not None:             # multi-step CPU baselines carry Adam / RMSprop state across learn() calls
+        opt.load_state_dict(opt_state)
     A, K = hp["action_size"], hp["num_support"]
     v_min, v_max = hp["v_min"], hp["v_max"]
     delta_z = (v_max - v_min) / (K - 1)
@@ -148,10 +153,11 @@ def dist_learn(params, target_params, batch, hp, optim):
         loss = KL.mean()
     opt.zero_grad(set_to_none=True)
     loss.backward()
-    out["grads"] = {k: v.grad.clone() for k, v in p.items()}
+    out["grads"] = {k: (v.grad.clone() if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
     opt.step()
     out["params"] = {k: v.detach().clone() for k, v in p.items()}
     out["loss"] = loss.item()
     out["KL"] = KL.detach().clone()
     out["target_dist"] = target_dist.clone()
+    out["opt_state"] = opt.state_dict()
     return out
