@@ -312,12 +312,74 @@ __device__ __forceinline__ float4 dh2_quad(const float* drow, const float4 (&wr)
   return make_float4(hv.x > 0.f ? t.x : 0.f, hv.y > 0.f ? t.y : 0.f, hv.z > 0.f ? t.z : 0.f, hv.w > 0.f ? t.w : 0.f);
 }
 
+// ---- tcgen05 building blocks for the tensor-core forward phase (same descriptors as csrc/tc_gemm.cu) -----------------
+// Operand tiles live in shared memory in the UMMA canonical K-major SWIZZLE_128B layout: one 128-byte row (32 fp32 of K)
+// per tile row, eight rows per 1 KB atom, 16-byte chunk index XOR row-in-atom.
+__device__ __forceinline__ unsigned tc_tile_off(int row, int chunk) { return (unsigned)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+__device__ __forceinline__ unsigned long long tc_desc(unsigned smem_addr) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((smem_addr >> 4) & 0x3FFF);        // start address
+  d |= (unsigned long long)1 << 16;                            // leading byte offset (unused: swizzled K-major)
+  d |= (unsigned long long)((1024 >> 4) & 0x3FFF) << 32;       // stride byte offset: 1 KB between 8-row atoms
+  d |= (unsigned long long)1 << 46;                            // descriptor version (sm_100)
+  d |= (unsigned long long)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = 32
+constexpr unsigned TC_IDESC_N32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void tc_mma(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(unsigned mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "TCW_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TCW_DONE;\n\t"
+      "bra TCW_LOOP;\n\t"
+      "TCW_DONE:\n\t"
+      "}\n" ::"r"(mbar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+// the low part of the 3xTF32 split: x - trunc_tf32(x) (the tensor core truncates the raw fp32 word), rounded to tf32
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  unsigned o;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(o) : "f"(r));
+  return __uint_as_float(o);
+}
+constexpr int TC_A_BYTES = 2 * 128 * 128;        // one A chunk: hi | lo, each [128 rows][32 k] fp32 = 16 KB
+constexpr int TC_B_BYTES = 2 * 32 * 128;         // one B chunk: hi | lo, each [32 rows][32 k] fp32 = 4 KB
+constexpr int TC_NA = 3, TC_NB = 6;              // ring depths: A chunks are generated, B chunks stream in 5 ahead
+constexpr int TC_BAR_WORD = 1664;                // s_small word offset of the tensor-core mbarriers (16 x 8 bytes)
+
 // timing trace (debug; JB_FUSED_SKIP bit 8): clock64 at fixed points of the LAST step, per CTA, 32 slots
 __device__ long long g_trace[256 * 48];
 #define TR(i) do { if (trace && tid == 0) g_trace[cta * 48 + (i)] = clock64(); } while (0)
 
 struct HeadTab { const float* w[MAXO]; const float* b[MAXO]; float* gw[MAXO]; float* gb[MAXO]; };
 
+template <bool TC>
 __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats, int flags /* debug: bit 8 = trace */) {
   extern __shared__ __align__(16) float smem[];
   float* s_small = smem;                       // SMALL_FLOATS
@@ -335,6 +397,12 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   stp.init(s_small + 1058);                    // 8-byte mbarrier: parameter stash
   float* dvs = s_small + 1088;                 // [MAX_B] second candidate value-head gradient of every row (P3); norm partials (P5)
   float* hb = s_small + 1600;                  // [MAXO] head biases
+  // tensor-core forward phase (TC instantiation): operand rings inside R0..R1 (1 KB aligned), 10 mbarriers
+  // ([0..2] A chunk retired, [3..8] B chunk landed, [9] tile accumulated), 32 TMEM columns for the whole launch
+  unsigned tc_base = 0, tc_tmem = 0, tc_tiles = 0;
+  unsigned long long tc_g = 0;                 // chunks issued so far by this CTA: ring positions and mbarrier phases
+  const unsigned tc_bar = smem_u32(s_small + TC_BAR_WORD);
+  float* tcp = nullptr;                        // generic pointer to the ring base (epilogue scratch)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned int nctas = gridDim.x;
@@ -348,6 +416,22 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   const long long step0 = *a.step, cursor0 = *a.cursor;
   const float lr = *a.lr;
 
+  if (TC) {
+    tc_base = (smem_u32(R0) + 1023u) & ~1023u;
+    tcp = R0 + ((tc_base - smem_u32(R0)) >> 2);
+    if (tid == 0) {
+      for (int i = 0; i < 10; ++i) mbar_init(tc_bar + 8u * i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_small + 1700)), "r"(32u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    tc_tmem = *reinterpret_cast<volatile unsigned*>(s_small + 1700);
+  }
   HeadTab& ht = *reinterpret_cast<HeadTab*>(s_small + 896);   // 32 pointers: shared memory, not 64 live registers
   if (tid == 0) {
     int o = 0;
@@ -360,7 +444,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   __syncthreads();
 
   const int MT = B / 32, NTL = H / 32, NP = (NTL + 1) >> 1;
-  const int nJ1 = MT * NTL;          // P1 tiles
+  const int nJ1 = TC ? (B >> 7) * NTL : MT * NTL;   // P1 tiles: 128 x 32 on the tensor cores, else 32 x 32 FFMA tiles
   const int nJB = MT * NTL;          // dh1 tiles (same decomposition as P1: job -> (mt, kt))
   const int nJA = NTL * NP;          // pairs of dW2 tiles
   const int nJC = NTL;               // head weight-gradient column jobs
@@ -383,6 +467,13 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
     if (i >= w2_lo && i < w2_hi) {
       const int e = (int)(i - w2_lo) * 4, n = e / H, k = e - n * H;
       *reinterpret_cast<float4*>(&a.W2t[((size_t)(k >> 5) * H + n) * 32 + (k & 31)]) = v;
+      if (TC) {
+        // UMMA-ready images of W2 (hi | lo of the 3xTF32 split): tile (n / 32, k / 32) = [32 rows][32 k] in the swizzled
+        // K-major layout, so that a B chunk of the forward phase is ONE 4 KB bulk copy per image
+        float* img = a.W2img + ((size_t)(n >> 5) * (H >> 5) + (k >> 5)) * 1024 + (tc_tile_off(n & 31, (k & 31) >> 2) >> 2);
+        *reinterpret_cast<float4*>(img) = v;
+        *reinterpret_cast<float4*>(img + (size_t)H * H) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+      }
     }
   };
   for (long long i = lo + tid; i < hi; i += NT) shadow(i, p4[i]);   // published by the first grid barrier
@@ -426,7 +517,17 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   gather_rows();
   // state rows of this CTA's first P1 tile of step 0 (later steps: gathered under the Adam phase)
   bool xs_ready = false;
-  if (cta < nJ1) {
+  float xpre[MAXD];                              // TC: this thread's state row (row tid & 127 of the CTA's first tile)
+  int xpre_idx = 0;
+#pragma unroll
+  for (int i = 0; i < MAXD; ++i) xpre[i] = 0.f;
+  if (TC && cta < nJ1) {
+    xpre_idx = a.perm[cursor0 * (long long)B + (cta / NTL) * 128 + (tid & 127)];
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) if (i < D) xpre[i] = a.state[(size_t)xpre_idx * D + i];
+    xs_ready = true;
+  }
+  if (!TC && cta < nJ1) {
     if (tid < 32) sidx[tid] = a.perm[cursor0 * (long long)B + (cta / NTL) * 32 + tid];
     __syncthreads();
     for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[i * 32 + r] = i < D ? a.state[(size_t)sidx[r] * D + i] : 0.f; }
@@ -448,7 +549,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
     if (tid == 64) { stp.copy(PS + (MAXO + 1) * PK, a.b1, (unsigned)H * 4u); stp.copy(PS + MAXO * PK, a.b2, (unsigned)H * 4u); }
     if (tid >= 96 && tid < 96 + nout) stp.copy(PS + (tid - 96) * PK, ht.w[tid - 96], (unsigned)H * 4u);
     if (tid >= 128 && tid < 128 + nout) hb[tid - 128] = ldcg(ht.b[tid - 128]);
-    if (cta < nJ1) { stage_kc(st, R1, a.W2, H, (cta % NTL) * 32, 0, H); st.commit(); }
+    if (!TC && cta < nJ1) { stage_kc(st, R1, a.W2, H, (cta % NTL) * 32, 0, H); st.commit(); }
     TR(28);
     stp.wait();
     TR(29);
@@ -461,6 +562,144 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         if (!a.continuous) { d[3] = pg[q][3]; d[4] = pg[q][4]; }
       }
     }
+    if constexpr (TC) {
+      // ---- tensor-core forward: one 128 (minibatch rows) x 32 (hidden units) tile per job, K = H in chunks of 32.
+      // A chunk = h1[128 rows][32 k] = relu(x W1^T + b1), GENERATED straight into the UMMA layout (hi | lo of the 3xTF32
+      // split) by all threads; B chunk = hi | lo image of W2[n0..n0+32][32 k] (kept current by the Adam phase), one 8 KB
+      // pair of bulk copies five chunks ahead; thread 0 issues 4 x 3 tcgen05.mma (M128 N32 K8, kind::tf32) per chunk into
+      // 32 TMEM columns and commits to the chunk's mbarrier, which is what lets the generators reuse the A slot.
+      const int NKC = H >> 5;
+      for (int job = cta; job < nJ1; job += (int)nctas) {
+        const int mt = job / NTL, nt = job - mt * NTL, m0 = mt * 128, n0 = nt * 32;
+        const int r = tid & 127, half = tid >> 7;
+        auto issue_b = [&](int kc, unsigned long long g) {
+          const unsigned slot = (unsigned)(g % TC_NB);
+          const unsigned bar = tc_bar + 8u * (3u + slot), dst = tc_base + TC_NA * TC_A_BYTES + slot * TC_B_BYTES;
+          mbar_expect_tx(bar, TC_B_BYTES);
+          const float* src = a.W2img + ((size_t)nt * NKC + kc) * 1024;
+          bulk_g2s(dst, src, 4096u, bar);
+          bulk_g2s(dst + 4096u, src + (size_t)H * H, 4096u, bar);
+        };
+        if (tid == 0)
+          for (int kc = 0; kc < min(TC_NB - 1, NKC); ++kc) issue_b(kc, tc_g + kc);
+        float xr[MAXD];
+        int xidx;
+        if (job == cta && xs_ready) {
+          xidx = xpre_idx;
+#pragma unroll
+          for (int i = 0; i < MAXD; ++i) xr[i] = xpre[i];
+        } else {
+          xidx = a.perm[(cursor0 + s) * (long long)B + m0 + r];
+#pragma unroll
+          for (int i = 0; i < MAXD; ++i) xr[i] = i < D ? a.state[(size_t)xidx * D + i] : 0.f;
+        }
+        if (nt == 0 && half == 0) {
+          a.cur_idx[m0 + r] = xidx;
+          for (int i = 0; i < D; ++i) a.xg[(size_t)(m0 + r) * D + i] = xr[i];
+        }
+        const float* W1s = R2;
+        const float* b1s = PS + (MAXO + 1) * PK;
+        TR(1);
+        for (int kc = 0; kc < NKC; ++kc) {
+          const unsigned long long g = tc_g + kc;
+          const unsigned abuf = tc_base + (unsigned)(g % TC_NA) * TC_A_BYTES;
+          if (g >= TC_NA) mbar_wait(tc_bar + 8u * (unsigned)(g % TC_NA), (unsigned)((g / TC_NA - 1) & 1));   // chunk g - 3 retired
+          float hv[16];
+          const int kb = kc * 32 + half * 16;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float h = 0.f;
+#pragma unroll
+            for (int i = 0; i < MAXD; ++i) if (i < D) h = fmaf(xr[i], W1s[(kb + j) * D + i], h);
+            hv[j] = fmaxf(h + b1s[kb + j], 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const unsigned off = tc_tile_off(r, half * 4 + c);
+            const float4 hi = make_float4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
+            const float4 lo = make_float4(tf32_lo(hi.x), tf32_lo(hi.y), tf32_lo(hi.z), tf32_lo(hi.w));
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(abuf + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(abuf + 16384u + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            if (nt == 0) *reinterpret_cast<float4*>(a.h1 + ((size_t)kc * B + m0 + r) * 32 + half * 16 + 4 * c) = hi;   // tiled [H/32][B][32]
+          }
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> async proxy (UMMA reads)
+          __syncthreads();
+          if (tid == 0) {
+            const unsigned slot = (unsigned)(g % TC_NB);
+            mbar_wait(tc_bar + 8u * (3u + slot), (unsigned)((g / TC_NB) & 1));            // B chunk landed
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const unsigned bbuf = tc_base + TC_NA * TC_A_BYTES + slot * TC_B_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const unsigned ko = 32u * j;                                               // K = 8 tf32 = 32 bytes inside the swizzled row
+              tc_mma(tc_tmem, tc_desc(abuf + ko), tc_desc(bbuf + ko), TC_IDESC_N32, (kc > 0 || j > 0) ? 1u : 0u);
+              tc_mma(tc_tmem, tc_desc(abuf + ko), tc_desc(bbuf + 4096u + ko), TC_IDESC_N32, 1u);
+              tc_mma(tc_tmem, tc_desc(abuf + 16384u + ko), tc_desc(bbuf + ko), TC_IDESC_N32, 1u);
+            }
+            tc_commit(tc_bar + 8u * (unsigned)(g % TC_NA));
+            if (kc == NKC - 1) tc_commit(tc_bar + 8u * 9u);
+            if (kc + TC_NB - 1 < NKC) {              // refill the B ring: chunk kc + 5 goes where chunk kc - 1 lived
+              if (kc >= 1) mbar_wait(tc_bar + 8u * (unsigned)((g - 1) % TC_NA), (unsigned)(((g - 1) / TC_NA) & 1));
+              issue_b(kc + TC_NB - 1, g + TC_NB - 1);
+            }
+          }
+        }
+        TR(3);
+        // ---- epilogue: TMEM -> registers (warp w: lanes 32 (w & 3).., columns 16 (w >> 2)..), bias + relu, h2 in both layouts,
+        // partial head outputs of the tile's 32 columns
+        mbar_wait(tc_bar + 8u * 9u, tc_tiles & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        {
+          const int q = warp & 3, cb = (warp >> 2) * 16, row = m0 + q * 32 + lane;
+          unsigned rr[16];
+          const unsigned taddr = tc_tmem + ((unsigned)(q * 32) << 16) + (unsigned)cb;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+              : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]),
+                "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(rr[i]) + PS[MAXO * PK + n0 + cb + i], 0.f);
+          float4* o2 = reinterpret_cast<float4*>(a.h2 + (size_t)row * H + n0 + cb);
+          float4* o2t = reinterpret_cast<float4*>(a.h2t + ((size_t)nt * B + row) * 32 + cb);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 t = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            o2[c] = t; o2t[c] = t;
+          }
+          float ph[MAXO];
+#pragma unroll
+          for (int o = 0; o < MAXO; ++o) {
+            float t = 0.f;
+            if (o < nout) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) t = fmaf(v[i], PS[o * PK + n0 + cb + i], t);
+            }
+            ph[o] = t;
+          }
+          float* sc = tcp + (q * 32 + lane) * MAXO;              // ring slot 0: every MMA that read it has retired
+          if (warp >= 4) {
+            *reinterpret_cast<float4*>(sc) = make_float4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<float4*>(sc + 4) = make_float4(ph[4], ph[5], ph[6], ph[7]);
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          __syncthreads();
+          if (warp < 4) {
+            const float4 u0 = *reinterpret_cast<const float4*>(sc), u1 = *reinterpret_cast<const float4*>(sc + 4);
+            *reinterpret_cast<float4*>(a.headp + (((size_t)nt * 2 + 0) * B + row) * 4) = make_float4(ph[0] + u0.x, ph[1] + u0.y, ph[2] + u0.z, ph[3] + u0.w);
+            if (nq > 1)
+              *reinterpret_cast<float4*>(a.headp + (((size_t)nt * 2 + 1) * B + row) * 4) = make_float4(ph[4] + u1.x, ph[5] + u1.y, ph[6] + u1.z, ph[7] + u1.w);
+          }
+          __syncthreads();
+        }
+        tc_g += (unsigned long long)NKC;
+        tc_tiles += 1u;
+        TR(4);
+      }
+    } else
     for (int job = cta; job < nJ1; job += (int)nctas) {
       const int mt = job / NTL, nt = job - mt * NTL;
       const int m0 = mt * 32, n0 = nt * 32;
@@ -567,7 +806,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
     // row ids of the NEXT step's first P1 tile: the load is in flight during the whole phase
     const bool has_next = (s + 1 < a.n_steps) && cta < nJ1;
     int next_r = 0;
-    if (has_next && tid < 32) next_r = a.perm[(cursor0 + s + 1) * (long long)B + (cta / NTL) * 32 + tid];
+    if (TC) { if (has_next) next_r = a.perm[(cursor0 + s + 1) * (long long)B + (cta / NTL) * 128 + (tid & 127)]; }
+    else if (has_next && tid < 32) next_r = a.perm[(cursor0 + s + 1) * (long long)B + (cta / NTL) * 32 + tid];
     if (s + 1 < a.n_steps) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) pr[q] = tid + q * NT < B ? a.perm[(cursor0 + s + 1) * (long long)B + tid + q * NT] : 0;
@@ -684,7 +924,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
 #pragma unroll
         for (int o = 0; o < MAXO; ++o)
           wr[o] = (o < nout && c4 < H) ? *reinterpret_cast<const float4*>(&PS[o * PK + c4]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!(job == cta && nJ1 <= (int)nctas))    // else xs still holds these rows from this CTA's P1 tile
+        if (TC || !(job == cta && nJ1 <= (int)nctas))    // else xs still holds these rows from this CTA's P1 tile
           for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[i * 32 + r] = i < D ? ldcg(a.xg + (size_t)(m0 + r) * D + i) : 0.f; }
         float h1m[4];                              // relu mask of the output tile: asm volatile keeps the loads HERE
 #pragma unroll
@@ -882,7 +1122,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       const float tot = block_sum(sq, scr + 64);
       if (tid == 0) a.partials[cta] = tot;
     }
-    if (has_next && tid < 32) sidx[tid] = next_r;
+    if (!TC && has_next && tid < 32) sidx[tid] = next_r;
     // Adam operands that do not depend on this step's gradient: in registers across the barrier
     float4 pp[ADAM_IT], mm[ADAM_IT], vv[ADAM_IT];
 #pragma unroll
@@ -968,7 +1208,13 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       }
       // next step's state rows (sidx was published before the barrier)
       float xv[2] = {0.f, 0.f};
-      if (has_next) {
+      if (TC) {
+        if (has_next) {
+          xpre_idx = next_r;
+#pragma unroll
+          for (int i = 0; i < MAXD; ++i) if (i < D) xpre[i] = a.state[(size_t)next_r * D + i];
+        }
+      } else if (has_next) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) { const int e = tid + q * NT, r = e >> 4, i = e & 15; if (i < D) xv[q] = a.state[(size_t)sidx[r] * D + i]; }
       }
@@ -1029,8 +1275,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         shadow(i, p_);
       }
       if (has_next) {
+        if (!TC) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) { const int e = tid + q * NT; xs[(e & 15) * 32 + (e >> 4)] = xv[q]; }
+          for (int q = 0; q < 2; ++q) { const int e = tid + q * NT; xs[(e & 15) * 32 + (e >> 4)] = xv[q]; }
+        }
         xs_ready = true;
       }
     }
@@ -1039,20 +1287,26 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
     TR(27);
   }
   if (cta == 0 && tid == 0) { *a.step = step0 + a.n_steps; *a.cursor = cursor0 + a.n_steps; }
+  if (TC) {
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tc_tmem), "r"(32u) : "memory");
+  }
 }
 
 static int dsm_floats_for(int B) { return B * MAXO; }
 static size_t fused_smem(int B) { return sizeof(float) * (size_t)(SMALL_FLOATS + dsm_floats_for(B) + 2 * RED_FLOATS + R2_FLOATS + PS_FLOATS); }
 
 // Largest grid the cooperative launch can keep co-resident (one CTA per SM on B200) for minibatch size B.
-static int fused_max_ctas(int B) {
+static int fused_max_ctas(int B, bool tc = false) {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t smem = fused_smem(B);
   if (smem > 227 * 1024) return 0;
-  cudaFuncSetAttribute(ppo_epoch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppo_epoch_kernel, NT, smem);
+  const void* fn = tc ? (const void*)ppo_epoch_kernel<true> : (const void*)ppo_epoch_kernel<false>;
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT, smem);
   return sms * (per_sm > 0 ? 1 : 0);
 }
 
@@ -1075,7 +1329,10 @@ JB_API int jb_ppo_fused_run(const void* host_args, void* stream) {
   if (a.B <= 0 || a.B % 32 || a.B > MAX_B || a.H <= 0 || a.H % 32 || a.H > PK || a.D <= 0 || a.D > MAXD || a.nout <= 0 ||
       a.nout > MAXO || a.A <= 0 || a.A > jbppo::MAX_A || a.n_steps <= 0 || a.P4 <= 0)
     return JB_ERR_INVALID;
-  int ctas = fused_max_ctas(a.B);
+  // tensor-core forward phase: 128-row tiles (B % 128 == 0) and the W2 image workspace; JB_FUSED_NO_TC=1 forces FFMA tiles
+  bool tc = a.B % 128 == 0 && a.W2img != nullptr;
+  if (const char* e = getenv("JB_FUSED_NO_TC")) tc = tc && atoi(e) == 0;
+  int ctas = fused_max_ctas(a.B, tc);
   if (ctas <= 0) return JB_ERR_INVALID;
   if (ctas > NT) ctas = NT;
   if (a.world < 1 || a.world > 8 || a.rank < 0 || a.rank >= a.world) return JB_ERR_INVALID;
@@ -1092,7 +1349,8 @@ JB_API int jb_ppo_fused_run(const void* host_args, void* stream) {
   int flags = 0;
   if (const char* e = getenv("JB_FUSED_SKIP")) flags = atoi(e);     // bit 8: record the timing trace
   void* kargs[] = {&a, &dsm_floats, &flags};
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)ppo_epoch_kernel, dim3(ctas), dim3(NT), kargs, smem, s);
+  cudaError_t e = cudaLaunchCooperativeKernel(tc ? (void*)ppo_epoch_kernel<true> : (void*)ppo_epoch_kernel<false>, dim3(ctas), dim3(NT),
+                                              kargs, smem, s);
   if (e != cudaSuccess) { cudaGetLastError(); return JB_ERR_CUDA; }
   return JB_OK;
 }

@@ -4,11 +4,11 @@
   ncu --clock-control none --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,\
 lts__t_bytes.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,dram__throughput.avg.pct_of_peak_sustained_elapsed,\
 launch__registers_per_thread,launch__grid_size,launch__block_size \
-      --nvtx --nvtx-include "jb/" -o gpurun_out/r02_kernels python scripts/ncu_kernels.py
+      --profile-from-start off -o gpurun_out/r02_kernels python scripts/ncu_kernels.py
 
-Every section runs inside an NVTX range "jb/<section>" so that only OUR launches (and the few torch fills inside the
-ranges) are captured; each section first runs once OUTSIDE the range to allocate workspaces and warm caches-that-matter
-(none: ncu flushes caches per replay), then once inside.
+Every section runs once UNPROFILED (allocates workspaces; ncu flushes caches per replay anyway), then once between
+cudaProfilerStart/Stop, so that only OUR launches (and the few torch fills next to them) are captured; the section
+name is printed in order, and an NVTX range carries it into the report.
 """
 import os
 import sys
@@ -35,9 +35,11 @@ class section:
             return fn
         fn()                                      # warm-up / allocation pass, not captured
         torch.cuda.synchronize()
-        torch.cuda.nvtx.range_push("jb/" + self.name)
+        torch.cuda.nvtx.range_push("jbsec_" + self.name)
+        torch.cuda.cudart().cudaProfilerStart()
         fn()
         torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
         torch.cuda.nvtx.range_pop()
         print("section", self.name, "done", flush=True)
         return fn

@@ -7,7 +7,7 @@ from jorldy_b200.core import Agent, Env
 from jorldy_b200.core.collect import RolloutCollector
 from jorldy_b200._lib import C
 
-N, T, B = 4096, 32, 256
+N, T, B = 4096, 32, int(os.environ.get("B", 256))
 env = Env("cartpole", num_envs=N, seed=0)
 agent = Agent("ppo", state_size=4, action_size=2, hidden_size=512, batch_size=B, n_step=T, n_epoch=1,
               optim_config={"name": "adam", "lr": 2.5e-4}, device="cuda", run_step=10**9, use_fused=True)
