@@ -50,6 +50,7 @@ class FusedRunner:
             "barrier": torch.zeros(64, dtype=torch.int32, device=dev),
         }
         self.max_ctas = C.jb_ppo_fused_max_ctas()
+        self.n_runs = 0
 
     def run(self, st, n_steps):
         ag = self.agent
@@ -83,6 +84,16 @@ class FusedRunner:
         a.beta1, a.beta2, a.adam_eps = opt.betas[0], opt.betas[1], opt.eps
         a.max_norm = float(ag.clip_grad_norm) if ag.clip_grad_norm else 0.0
         p2p = getattr(ag, "p2p", None)
+        if p2p is not None and self.n_runs < 4:
+            # The kernel spins on flags written by the peers' kernels.  During the first launches the ranks' hosts are
+            # still far apart (lazy allocations, CUDA-graph capture of the collect loop, module loading), and a host
+            # call that has to wait for a peer DEVICE while that device spins on this rank's not-yet-launched kernel
+            # would deadlock until the kernel's time-out: meet on the host with idle GPUs, then launch at once.
+            import torch.distributed as dist
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+        self.n_runs += 1
         if p2p is not None:
             assert net.grad.data_ptr() == p2p["ptrs"][p2p["rank"]], "gradient buffer is not the peer-mapped exchange buffer"
             for r in range(8):

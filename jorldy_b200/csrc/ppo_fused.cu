@@ -342,17 +342,26 @@ __device__ __forceinline__ void tc_commit(unsigned mbar) {
 __device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
 }
+// Bounded: a tensor-core pipeline bug must fail the launch (trap -> CUDA error on the host), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  unsigned done = 0;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "TCW_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra TCW_DONE;\n\t"
-      "bra TCW_LOOP;\n\t"
-      "TCW_DONE:\n\t"
-      "}\n" ::"r"(mbar), "r"(parity)
-      : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  if (done) return;
+  const unsigned long long t0 = global_ns();
+  while (!done) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    if (!done && global_ns() - t0 > 2000000000ull) asm volatile("trap;\n");
+  }
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
@@ -379,7 +388,8 @@ __device__ long long g_trace[256 * 48];
 
 struct HeadTab { const float* w[MAXO]; const float* b[MAXO]; float* gw[MAXO]; float* gb[MAXO]; };
 
-template <bool TC>
+// TC: tensor-core forward phase (B % 128 == 0); NA: compile-time bound on the action count (row maths loop bound)
+template <bool TC, int NA>
 __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats, int flags /* debug: bit 8 = trace */) {
   extern __shared__ __align__(16) float smem[];
   float* s_small = smem;                       // SMALL_FLOATS
@@ -843,10 +853,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           TR(31);
           jbppo::RowOut ro;
           if (a.continuous)
-            jbppo::row<true>(ov, A, 0, (const float*)a.action + (size_t)r * A, g_adv, g_ret, g_vold,
+            jbppo::row<true, NA>(ov, A, 0, (const float*)a.action + (size_t)r * A, g_adv, g_ret, g_vold,
                              a.logp_old + (size_t)r * A, hp, invB, ro);
           else
-            jbppo::row<false>(ov, A, g_act, nullptr, g_adv, g_ret, g_vold, &g_lpo, hp, invB, ro);
+            jbppo::row<false, NA>(ov, A, g_act, nullptr, g_adv, g_ret, g_vold, &g_lpo, hp, invB, ro);
 #pragma unroll
           for (int o = 0; o < MAXO; ++o) dsm[b * MAXO + o] = o < npol ? ro.dpol[o] : 0.f;
           dsm[b * MAXO + npol] = ro.dv1; dvs[b] = ro.dv2;      // the two candidate value-head gradients, resolved below
@@ -1298,13 +1308,21 @@ static int dsm_floats_for(int B) { return B * MAXO; }
 static size_t fused_smem(int B) { return sizeof(float) * (size_t)(SMALL_FLOATS + dsm_floats_for(B) + 2 * RED_FLOATS + R2_FLOATS + PS_FLOATS); }
 
 // Largest grid the cooperative launch can keep co-resident (one CTA per SM on B200) for minibatch size B.
-static int fused_max_ctas(int B, bool tc = false) {
+static const void* fused_fn(bool tc, int A) {
+  const int na = A <= 2 ? 0 : (A <= 4 ? 1 : 2);
+  static const void* const tab[2][3] = {
+      {(const void*)ppo_epoch_kernel<false, 2>, (const void*)ppo_epoch_kernel<false, 4>, (const void*)ppo_epoch_kernel<false, 8>},
+      {(const void*)ppo_epoch_kernel<true, 2>, (const void*)ppo_epoch_kernel<true, 4>, (const void*)ppo_epoch_kernel<true, 8>}};
+  return tab[tc ? 1 : 0][na];
+}
+
+static int fused_max_ctas(int B, bool tc = false, int A = 8) {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t smem = fused_smem(B);
   if (smem > 227 * 1024) return 0;
-  const void* fn = tc ? (const void*)ppo_epoch_kernel<true> : (const void*)ppo_epoch_kernel<false>;
+  const void* fn = fused_fn(tc, A);
   cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT, smem);
   return sms * (per_sm > 0 ? 1 : 0);
@@ -1332,7 +1350,7 @@ JB_API int jb_ppo_fused_run(const void* host_args, void* stream) {
   // tensor-core forward phase: 128-row tiles (B % 128 == 0) and the W2 image workspace; JB_FUSED_NO_TC=1 forces FFMA tiles
   bool tc = a.B % 128 == 0 && a.W2img != nullptr;
   if (const char* e = getenv("JB_FUSED_NO_TC")) tc = tc && atoi(e) == 0;
-  int ctas = fused_max_ctas(a.B, tc);
+  int ctas = fused_max_ctas(a.B, tc, a.A);
   if (ctas <= 0) return JB_ERR_INVALID;
   if (ctas > NT) ctas = NT;
   if (a.world < 1 || a.world > 8 || a.rank < 0 || a.rank >= a.world) return JB_ERR_INVALID;
@@ -1349,8 +1367,7 @@ JB_API int jb_ppo_fused_run(const void* host_args, void* stream) {
   int flags = 0;
   if (const char* e = getenv("JB_FUSED_SKIP")) flags = atoi(e);     // bit 8: record the timing trace
   void* kargs[] = {&a, &dsm_floats, &flags};
-  cudaError_t e = cudaLaunchCooperativeKernel(tc ? (void*)ppo_epoch_kernel<true> : (void*)ppo_epoch_kernel<false>, dim3(ctas), dim3(NT),
-                                              kargs, smem, s);
+  cudaError_t e = cudaLaunchCooperativeKernel(const_cast<void*>(fused_fn(tc, a.A)), dim3(ctas), dim3(NT), kargs, smem, s);
   if (e != cudaSuccess) { cudaGetLastError(); return JB_ERR_CUDA; }
   return JB_OK;
 }

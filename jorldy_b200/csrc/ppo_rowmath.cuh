@@ -25,16 +25,19 @@ struct RowOut {
 // All per-action loops run over the compile-time bound MAX_A with an `a < A` guard: arrays stay in
 // registers (a run-time trip count would index them dynamically and put them in local memory) and the
 // arithmetic order is the plain ascending-a order of the restated definitions.
+template <int NA = MAX_A>
 __device__ __forceinline__ void log_softmax_row(const float (&lg)[MAX_A], int A, float (&lsm)[MAX_A]) {
   float mx = lg[0];
 #pragma unroll
-  for (int a = 1; a < MAX_A; ++a) if (a < A) mx = fmaxf(mx, lg[a]);
+  for (int a = 1; a < NA; ++a) if (a < A) mx = fmaxf(mx, lg[a]);
   float s = 0.f;
 #pragma unroll
-  for (int a = 0; a < MAX_A; ++a) if (a < A) s += expf(lg[a] - mx);
+  for (int a = 0; a < NA; ++a) if (a < A) s += expf(lg[a] - mx);
   const float ls = logf(s);
 #pragma unroll
-  for (int a = 0; a < MAX_A; ++a) lsm[a] = a < A ? (lg[a] - mx) - ls : 0.f;
+  for (int a = NA; a < MAX_A; ++a) lsm[a] = 0.f;
+#pragma unroll
+  for (int a = 0; a < NA; ++a) lsm[a] = a < A ? (lg[a] - mx) - ls : 0.f;
 }
 
 __device__ __forceinline__ float atanh_clamped(float a) {
@@ -55,12 +58,13 @@ __device__ __forceinline__ void surrogate(float ratio, float adv, float eps, flo
 
 // o: the row's head outputs [nout] (at least 2*MAX_A... entries readable up to index nout-1); a_disc / a_cont:
 // the stored action; lpo: log_prob_old (1 or A values)
-template <bool CONT>
+// NA: compile-time bound on A (the loops run to NA, guarded by a < A): row<., 2> costs a quarter of row<., 8>
+template <bool CONT, int NA = MAX_A>
 __device__ __forceinline__ void row(const float* o, int A, int a_disc, const float* a_cont, float adv, float ret,
                                     float vold, const float* lpo, HP hp, float invB, RowOut& r) {
   float v = 0.f;                                   // o[CONT ? 2A : A] without a run-time register index
 #pragma unroll
-  for (int q = 0; q < 2 * MAX_A + 1; ++q) if (q == (CONT ? 2 * A : A)) v = o[q];
+  for (int q = 0; q < 2 * NA + 1; ++q) if (q == (CONT ? 2 * A : A)) v = o[q];
   const float dv_raw = v - vold;
   const float vclip = vold + fminf(fmaxf(dv_raw, -hp.eps_clip), hp.eps_clip);
   const float in_clip = (dv_raw >= -hp.eps_clip && dv_raw <= hp.eps_clip) ? 1.f : 0.f;
@@ -73,14 +77,14 @@ __device__ __forceinline__ void row(const float* o, int A, int a_disc, const flo
   if (!CONT) {
     float lg[MAX_A], lsm[MAX_A], pi[MAX_A], p[MAX_A], lc[MAX_A], inr[MAX_A];
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) lg[a] = a < A ? o[a] : 0.f;
-    log_softmax_row(lg, A, lsm);
+    for (int a = 0; a < MAX_A; ++a) lg[a] = (a < NA && a < A) ? o[a] : 0.f;
+    log_softmax_row<NA>(lg, A, lsm);
     float S = 0.f;
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) { pi[a] = 0.f; if (a < A) { pi[a] = expf(lsm[a]); S += pi[a]; } }
+    for (int a = 0; a < NA; ++a) { pi[a] = 0.f; if (a < A) { pi[a] = expf(lsm[a]); S += pi[a]; } }
     float ent = 0.f, logp = 0.f;
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) {
+    for (int a = 0; a < NA; ++a) {
       p[a] = 1.f; lc[a] = 0.f; inr[a] = 0.f;
       if (a < A) {
         p[a] = pi[a] / S;
@@ -99,7 +103,7 @@ __device__ __forceinline__ void row(const float* o, int A, int a_disc, const flo
     const float dent = -hp.ent_coef * invB;            // d(ent_coef * entropy_loss)/d entropy_b
     float dp[MAX_A], dot = 0.f;
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) {
+    for (int a = 0; a < NA; ++a) {
       dp[a] = 0.f;
       if (a < A) {
         float t = dent * (-(lc[a] + inr[a]));
@@ -110,7 +114,7 @@ __device__ __forceinline__ void row(const float* o, int A, int a_disc, const flo
     }
     float dlsm[MAX_A], sum_dlsm = 0.f;
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) {
+    for (int a = 0; a < NA; ++a) {
       dlsm[a] = 0.f;
       if (a < A) {
         const float dpi = dp[a] / S - dot / (S * S);
@@ -119,22 +123,22 @@ __device__ __forceinline__ void row(const float* o, int A, int a_disc, const flo
       }
     }
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) if (a < A) r.dpol[a] = dlsm[a] - expf(lsm[a]) * sum_dlsm;
+    for (int a = 0; a < NA; ++a) if (a < A) r.dpol[a] = dlsm[a] - expf(lsm[a]) * sum_dlsm;
   } else {
     const float log_sqrt_2pi = 0.9189385332046727f;
     float dsum = 0.f, ent = 0.f;
     float omu[MAX_A], ols[MAX_A], mu[MAX_A], sd[MAX_A], ls[MAX_A], z[MAX_A], dmu_[MAX_A], dls_[MAX_A];
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) {                 // o[a] and o[A + a] without run-time register indices
+    for (int a = 0; a < NA; ++a) {                 // o[a] and o[A + a] without run-time register indices
       omu[a] = a < A ? o[a] : 0.f;
       float t = 0.f;
 #pragma unroll
-      for (int q = 0; q < 2 * MAX_A; ++q) if (q == A + a && a < A) t = o[q];
+      for (int q = 0; q < 2 * NA; ++q) if (q == A + a && a < A) t = o[q];
       ols[a] = t;
     }
     float pmin = INFINITY;
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) {
+    for (int a = 0; a < NA; ++a) {
       mu[a] = sd[a] = ls[a] = z[a] = 0.f;
       if (a < A) {
         mu[a] = fminf(fmaxf(omu[a], -5.f), 5.f);
@@ -155,7 +159,7 @@ __device__ __forceinline__ void row(const float* o, int A, int a_disc, const flo
     const float dlogp = -gr * ratio * invB;
     const float dent = -hp.ent_coef * invB / (float)A;   // entropy_loss = -mean over B*A elements
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) {
+    for (int a = 0; a < NA; ++a) {
       dmu_[a] = dls_[a] = 0.f;
       if (a < A) {
         const float d = z[a] - mu[a];
@@ -168,10 +172,10 @@ __device__ __forceinline__ void row(const float* o, int A, int a_disc, const flo
       }
     }
 #pragma unroll
-    for (int q = 0; q < 2 * MAX_A; ++q) {
+    for (int q = 0; q < 2 * NA; ++q) {
       float t = 0.f;
 #pragma unroll
-      for (int a = 0; a < MAX_A; ++a) {
+      for (int a = 0; a < NA; ++a) {
         if (a < A && q == a) t = dmu_[a];
         if (a < A && q == A + a) t = dls_[a];
       }
