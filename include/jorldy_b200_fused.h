@@ -28,6 +28,7 @@ typedef struct jb_ppo_fused_args {
   float *W2t;                        /* [H/32, H, 32] tiled shadow of W2 (maintained by the Adam phase) */
   float *W2img;                      /* [2 (hi | lo), H/32, H/32, 32 x 32] UMMA-layout images of W2 for the tensor-core
                                       * forward phase (3xTF32 split), maintained by the Adam phase; NULL: FFMA tiles only */
+  float *W2Timg;                     /* [2, H/128, H/32, 128 x 32] the same for W2^T (operand of the tensor-core dh1 jobs) */
   float *partials;                   /* [256] per-CTA squared-norm partials */
   float *acc;                        /* [8] learn()-level statistic accumulators */
   int32_t *cur_idx;                  /* [B] */

@@ -380,7 +380,9 @@ __device__ __forceinline__ float tf32_lo(float x) {
 constexpr int TC_A_BYTES = 2 * 128 * 128;        // one A chunk: hi | lo, each [128 rows][32 k] fp32 = 16 KB
 constexpr int TC_B_BYTES = 2 * 32 * 128;         // one B chunk: hi | lo, each [32 rows][32 k] fp32 = 4 KB
 constexpr int TC_NA = 3, TC_NB = 6;              // ring depths: A chunks are generated, B chunks stream in 5 ahead
-constexpr int TC_BAR_WORD = 1664;                // s_small word offset of the tensor-core mbarriers (16 x 8 bytes)
+constexpr int TC_BAR_WORD = 1664;                // s_small word offset of the tensor-core mbarriers (32 x 8 bytes)
+constexpr int TC_TMEM_WORD = 1660;               // s_small word that receives the TMEM base address
+constexpr int TC_NBAR = 24;                      // [0..9] forward, [10..15] dh1 jobs, [16..23] dW2 jobs
 
 // timing trace (debug; JB_FUSED_SKIP bit 8): clock64 at fixed points of the LAST step, per CTA, 32 slots
 __device__ long long g_trace[256 * 48];
@@ -411,6 +413,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   // ([0..2] A chunk retired, [3..8] B chunk landed, [9] tile accumulated), 32 TMEM columns for the whole launch
   unsigned tc_base = 0, tc_tmem = 0, tc_tiles = 0;
   unsigned long long tc_g = 0;                 // chunks issued so far by this CTA: ring positions and mbarrier phases
+  unsigned long long jb_g = 0;                 // same for the tensor-core dh1 jobs (mbarriers 10..15)
   const unsigned tc_bar = smem_u32(s_small + TC_BAR_WORD);
   float* tcp = nullptr;                        // generic pointer to the ring base (epilogue scratch)
 
@@ -430,17 +433,17 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
     tc_base = (smem_u32(R0) + 1023u) & ~1023u;
     tcp = R0 + ((tc_base - smem_u32(R0)) >> 2);
     if (tid == 0) {
-      for (int i = 0; i < 10; ++i) mbar_init(tc_bar + 8u * i, 1);
+      for (int i = 0; i < TC_NBAR; ++i) mbar_init(tc_bar + 8u * i, 1);
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_small + 1700)), "r"(32u) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_small + TC_TMEM_WORD)), "r"(32u) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    tc_tmem = *reinterpret_cast<volatile unsigned*>(s_small + 1700);
+    tc_tmem = *reinterpret_cast<volatile unsigned*>(s_small + TC_TMEM_WORD);
   }
   HeadTab& ht = *reinterpret_cast<HeadTab*>(s_small + 896);   // 32 pointers: shared memory, not 64 live registers
   if (tid == 0) {
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
 
   const int MT = B / 32, NTL = H / 32, NP = (NTL + 1) >> 1;
   const int nJ1 = TC ? (B >> 7) * NTL : MT * NTL;   // P1 tiles: 128 x 32 on the tensor cores, else 32 x 32 FFMA tiles
-  const int nJB = MT * NTL;          // dh1 tiles (same decomposition as P1: job -> (mt, kt))
+  const int nJB = TC ? (H >> 7) * MT : MT * NTL;   // dh1 tiles: TC 128 (hidden units) x 32 (rows), else 32 x 32 like P1
   const int nJA = NTL * NP;          // pairs of dW2 tiles
   const int nJC = NTL;               // head weight-gradient column jobs
   const int nJD = NTL;               // dW1 / db1 folds
@@ -483,6 +486,15 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         float* img = a.W2img + ((size_t)(n >> 5) * (H >> 5) + (k >> 5)) * 1024 + (tc_tile_off(n & 31, (k & 31) >> 2) >> 2);
         *reinterpret_cast<float4*>(img) = v;
         *reinterpret_cast<float4*>(img + (size_t)H * H) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        // ... and of W2^T for the dh1 jobs: tile (k / 128, n / 32) = [128 rows k][32 columns n]
+        const float vv4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int kk = k + q;
+          float* t = a.W2Timg + ((size_t)(kk >> 7) * (H >> 5) + (n >> 5)) * 4096 + (tc_tile_off(kk & 127, (n & 31) >> 2) >> 2) + (n & 3);
+          t[0] = vv4[q];
+          t[(size_t)H * H] = tf32_lo(vv4[q]);
+        }
       }
     }
   };
@@ -491,6 +503,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
 
   auto issue_stage = [&](int job) {          // first-panel cp.async of a backward job (JD has none)
     if (job < nJB) {
+      if (TC) return;                          // tensor-core dh1 jobs run their own operand rings
       const int mt = job / NTL, kt = job - mt * NTL;
       stage_kc(st, R0, a.h2, H, mt * 32, 0, H);
       stage_block(st, R1, a.W2t + (size_t)kt * H * 32, H);
@@ -544,6 +557,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
     xs_ready = true;
   }
   __syncthreads();
+
+  if (TC) grid_bar(a.barrier, epoch, nctas);     // the W2 images built above are read by the FIRST forward phase
 
   for (int s = 0; s < a.n_steps; ++s) {
     const bool trace = (flags & 256) && s == a.n_steps - 1;
@@ -813,6 +828,19 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
     // =========================== P3: row phase + backward jobs =========================================
     int pre_job = -1;                              // job whose first panels are already in flight
     if (cta < nJ3 && (cta < nJB || prefetchable(cta))) { issue_stage(cta); pre_job = cta; }
+    // tensor-core dh1 job: the first two W2^T chunks do not depend on the row phase, fetch them under it
+    auto jb_issue_a = [&](int kt4, int nc, unsigned long long g) {
+      const unsigned slot = (unsigned)(g % TC_NA);
+      const unsigned bar = tc_bar + 8u * (13u + slot), dst = tc_base + slot * TC_A_BYTES;
+      mbar_expect_tx(bar, TC_A_BYTES);
+      const float* src = a.W2Timg + ((size_t)kt4 * (H >> 5) + nc) * 4096;
+      bulk_g2s(dst, src, 16384u, bar);
+      bulk_g2s(dst + 16384u, src + (size_t)H * H, 16384u, bar);
+    };
+    if (TC && cta < nJB && tid == 0) {
+      jb_issue_a(cta / MT, 0, jb_g);
+      if ((H >> 5) > 1) jb_issue_a(cta / MT, 1, jb_g + 1);
+    }
     // row ids of the NEXT step's first P1 tile: the load is in flight during the whole phase
     const bool has_next = (s + 1 < a.n_steps) && cta < nJ1;
     int next_r = 0;
@@ -924,7 +952,109 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       __syncthreads();
       TR(8 + min(3, (job - cta) / (int)nctas));
       const int next = job + (int)nctas;
-      if (job < nJB) {
+      if (TC && job < nJB) {
+        // ---- tensor-core dh1 job: D[128 hidden units k][32 rows m] = sum_n W2[n][k] dh2[m][n]  (dh1 transposed) ---------
+        // A chunk = hi | lo image of W2^T [128 k][32 n] (two 16 KB bulk copies, two chunks ahead); B chunk = dh2^T
+        // [32 m][32 n] = ((dout Wh) * relu'(h2)) generated by the threads, ONE float4 each; 4 x 3 tcgen05.mma per chunk.
+        // Epilogue: mask by relu'(h1) (h1 recomputed from x: D FMAs), partial dW1 / db1 of this 32-row tile.
+        const int kt4 = job / MT, mt = job - kt4 * MT, m0 = mt * 32, kin0 = kt4 * 128, NKC = H >> 5;
+        if (job != cta && tid == 0) {
+          jb_issue_a(kt4, 0, jb_g);
+          if (NKC > 1) jb_issue_a(kt4, 1, jb_g + 1);
+        }
+        for (int e = tid; e < 32 * MAXD; e += NT) { const int r = e >> 4, i = e & 15; xs[i * 32 + r] = i < D ? ldcg(a.xg + (size_t)(m0 + r) * D + i) : 0.f; }
+        const int ml = tid >> 3, c8 = tid & 7;                      // this thread's element group: row m0 + ml, columns 4 c8 .. + 3 of a chunk
+        const float* drow = &dsm[(m0 + ml) * MAXO];
+        float4 hq = ldcg4(a.h2 + (size_t)(m0 + ml) * H + 4 * c8);     // h2 of chunk 0 (prefetched one chunk ahead below)
+        for (int nc = 0; nc < NKC; ++nc) {
+          const unsigned long long g = jb_g + nc;
+          const unsigned slot = (unsigned)(g % TC_NA);
+          if (g >= TC_NA) mbar_wait(tc_bar + 8u * (10u + slot), (unsigned)((g / TC_NA - 1) & 1));     // chunk g - 3 retired: B slot free
+          float4 wr[MAXO];
+#pragma unroll
+          for (int o = 0; o < MAXO; ++o) wr[o] = o < nout ? *reinterpret_cast<const float4*>(&PS[o * PK + nc * 32 + 4 * c8]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 hcur = hq;
+          if (nc + 1 < NKC) hq = ldcg4(a.h2 + (size_t)(m0 + ml) * H + (nc + 1) * 32 + 4 * c8);
+          const float4 dv = dh2_quad(drow, wr, hcur);
+          const float4 lo = make_float4(tf32_lo(dv.x), tf32_lo(dv.y), tf32_lo(dv.z), tf32_lo(dv.w));
+          const unsigned bbuf = tc_base + TC_NA * TC_A_BYTES + slot * TC_B_BYTES, off = tc_tile_off(ml, c8);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(bbuf + off), "f"(dv.x), "f"(dv.y), "f"(dv.z), "f"(dv.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(bbuf + 4096u + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          __syncthreads();
+          if (tid == 0) {
+            mbar_wait(tc_bar + 8u * (13u + slot), (unsigned)((g / TC_NA) & 1));               // W2^T chunk landed
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const unsigned abuf = tc_base + slot * TC_A_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const unsigned ko = 32u * j;
+              tc_mma(tc_tmem, tc_desc(abuf + ko), tc_desc(bbuf + ko), TC_IDESC_N32, (nc > 0 || j > 0) ? 1u : 0u);
+              tc_mma(tc_tmem, tc_desc(abuf + ko), tc_desc(bbuf + 4096u + ko), TC_IDESC_N32, 1u);
+              tc_mma(tc_tmem, tc_desc(abuf + 16384u + ko), tc_desc(bbuf + ko), TC_IDESC_N32, 1u);
+            }
+            tc_commit(tc_bar + 8u * (10u + slot));
+            if (nc == NKC - 1) tc_commit(tc_bar + 8u * 9u);
+            if (nc + 2 < NKC) {                      // A ring: chunk nc + 2 goes where chunk nc - 1 lived
+              if (nc >= 1) mbar_wait(tc_bar + 8u * (10u + (unsigned)((g - 1) % TC_NA)), (unsigned)(((g - 1) / TC_NA) & 1));
+              jb_issue_a(kt4, nc + 2, g + 2);
+            }
+          }
+        }
+        mbar_wait(tc_bar + 8u * 9u, tc_tiles & 1u);                 // (the "tile accumulated" barrier is shared with the forward phase)
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        if (prefetchable(next)) { issue_stage(next); pre_job = next; }   // every MMA that read the rings has retired
+        {
+          const int q = warp & 3, cb = (warp >> 2) * 16, kin = kin0 + q * 32 + lane;
+          unsigned rr[16];
+          const unsigned taddr = tc_tmem + ((unsigned)(q * 32) << 16) + (unsigned)cb;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+              : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]),
+                "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          // h1[m][kin] > 0 ?  (same arithmetic as the forward phase: fma chain over the inputs, then + b1)
+          float w1r[MAXD];
+#pragma unroll
+          for (int i = 0; i < MAXD; ++i) w1r[i] = i < D ? ldcg(a.W1 + (size_t)kin * D + i) : 0.f;
+          const float b1v = PS[(MAXO + 1) * PK + kin];
+          float wacc[MAXD + 1];
+#pragma unroll
+          for (int i = 0; i <= MAXD; ++i) wacc[i] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ml2 = cb + j;
+            float h = 0.f;
+#pragma unroll
+            for (int i = 0; i < MAXD; ++i) if (i < D) h = fmaf(xs[i * 32 + ml2], w1r[i], h);
+            const float dvv = (h + b1v > 0.f) ? __uint_as_float(rr[j]) : 0.f;
+#pragma unroll
+            for (int i = 0; i < MAXD; ++i) if (i < D) wacc[i] = fmaf(dvv, xs[i * 32 + ml2], wacc[i]);
+            wacc[MAXD] += dvv;
+          }
+          float* sc = tcp + (size_t)(q * 32 + lane) * (MAXD + 1);       // [128 k][MAXD + 1] scratch in ring slot 0
+          if (warp >= 4) {
+#pragma unroll
+            for (int i = 0; i <= MAXD; ++i) if (i < D || i == MAXD) sc[i] = wacc[i];
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          __syncthreads();
+          if (warp < 4) {
+            float* dstw = a.w1p + ((size_t)mt * H + kin) * (D + 1);
+#pragma unroll
+            for (int i = 0; i < MAXD; ++i) if (i < D) dstw[i] = wacc[i] + sc[i];
+            dstw[D] = wacc[MAXD] + sc[MAXD];
+          }
+          __syncthreads();
+        }
+        if (tid < 4) asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(a.barrier + CTR_JB + kt4 * 4 + tid) : "memory");
+        jb_g += (unsigned long long)NKC;
+        tc_tiles += 1u;
+        TR(16);
+      } else if (job < nJB) {
         // ---- dh1 tile = ((dout Wh) * relu'(h2)) W2, masked by relu'(h1); partial dW1 / db1 ---------------
         const int mt = job / NTL, kt = job - mt * NTL;
         const int m0 = mt * 32, k0 = kt * 32;
@@ -1348,7 +1478,7 @@ JB_API int jb_ppo_fused_run(const void* host_args, void* stream) {
       a.nout > MAXO || a.A <= 0 || a.A > jbppo::MAX_A || a.n_steps <= 0 || a.P4 <= 0)
     return JB_ERR_INVALID;
   // tensor-core forward phase: 128-row tiles (B % 128 == 0) and the W2 image workspace; JB_FUSED_NO_TC=1 forces FFMA tiles
-  bool tc = a.B % 128 == 0 && a.W2img != nullptr;
+  bool tc = a.B % 128 == 0 && a.H % 128 == 0 && a.W2img != nullptr && a.W2Timg != nullptr;
   if (const char* e = getenv("JB_FUSED_NO_TC")) tc = tc && atoi(e) == 0;
   int ctas = fused_max_ctas(a.B, tc, a.A);
   if (ctas <= 0) return JB_ERR_INVALID;
