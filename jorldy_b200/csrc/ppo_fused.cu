@@ -121,19 +121,14 @@ struct Stager {
 // ---- cross-GPU flag wait (multi-GPU gradient exchange): bounded by WALL-CLOCK time (a peer may legitimately be
 // seconds late: it is another process with its own host-side launch sequence), and once one wait has given up every
 // later wait returns at once (`abort_flag`, a word of this GPU's barrier block), so that a dead peer costs one timeout
-// per launch instead of one per step; the host then raises (ppo.py checks acc[7]).
-constexpr unsigned long long X_TIMEOUT_NS = 60ull * 1000ull * 1000ull * 1000ull;
+// per launch instead of one per step; the host then raises (ppo.py checks acc[7]).  Time = SM cycles (clock64).
+constexpr long long X_TIMEOUT_CYCLES = 60ll * 1965000000ll;   // ~60 s of SM clock (clock64: a register read)
 constexpr int CTR_ABORT = 63;                           // a.barrier[CTR_ABORT] != 0: an exchange wait timed out
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
-  return t;
-}
 __device__ __forceinline__ bool sys_flag_wait(const unsigned int* flag, unsigned int target, unsigned int* abort_flag) {
   unsigned int v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
   if ((int)(v - target) >= 0) return true;
-  const unsigned long long t0 = global_ns();
+  const long long t0 = clock64();
   for (;;) {
     for (int it = 0; it < 32; ++it) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
@@ -142,7 +137,7 @@ __device__ __forceinline__ bool sys_flag_wait(const unsigned int* flag, unsigned
     unsigned int ab;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(ab) : "l"(abort_flag) : "memory");
     if (ab) return false;
-    if (global_ns() - t0 > X_TIMEOUT_NS) {
+    if (clock64() - t0 > X_TIMEOUT_CYCLES) {
       asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(abort_flag), "r"(1u) : "memory");
       return false;
     }
@@ -342,25 +337,21 @@ __device__ __forceinline__ void tc_commit(unsigned mbar) {
 __device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
 }
-// Bounded: a tensor-core pipeline bug must fail the launch (trap -> CUDA error on the host), never hang the GPU.
+// Bounded: a tensor-core pipeline bug must fail the launch (trap -> CUDA error on the host), never hang the GPU.  The
+// bound is counted in SM clock cycles (clock64 is a register read; %globaltimer costs microseconds per read, which made
+// every wait that missed its first try a 2-5 us stall).
 __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
   unsigned done = 0;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-  if (done) return;
-  const unsigned long long t0 = global_ns();
-  while (!done) {
+  const long long t0 = clock64();
+  for (;;) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-    if (!done && global_ns() - t0 > 2000000000ull) asm volatile("trap;\n");
+    if (done) return;
+    if (clock64() - t0 > (1ll << 32)) asm volatile("trap;\n");      // ~2 s
   }
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
@@ -414,6 +405,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   unsigned tc_base = 0, tc_tmem = 0, tc_tiles = 0;
   unsigned long long tc_g = 0;                 // chunks issued so far by this CTA: ring positions and mbarrier phases
   unsigned long long jb_g = 0;                 // same for the tensor-core dh1 jobs (mbarriers 10..15)
+  unsigned long long ja_g = 0;                 // ... and the dW2 jobs (mbarriers 16..18)
   const unsigned tc_bar = smem_u32(s_small + TC_BAR_WORD);
   float* tcp = nullptr;                        // generic pointer to the ring base (epilogue scratch)
 
@@ -459,7 +451,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   const int MT = B / 32, NTL = H / 32, NP = (NTL + 1) >> 1;
   const int nJ1 = TC ? (B >> 7) * NTL : MT * NTL;   // P1 tiles: 128 x 32 on the tensor cores, else 32 x 32 FFMA tiles
   const int nJB = TC ? (H >> 7) * MT : MT * NTL;   // dh1 tiles: TC 128 (hidden units) x 32 (rows), else 32 x 32 like P1
-  const int nJA = NTL * NP;          // pairs of dW2 tiles
+  const int nJA = TC ? (H >> 7) * NTL : NTL * NP;   // dW2: TC 128 (k) x 32 (n) tiles of dW2^T, else pairs of 32 x 32 tiles
   const int nJC = NTL;               // head weight-gradient column jobs
   const int nJD = NTL;               // dW1 / db1 folds
   const int nJ3 = nJB + nJA + nJC + nJD;
@@ -508,6 +500,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       stage_kc(st, R0, a.h2, H, mt * 32, 0, H);
       stage_block(st, R1, a.W2t + (size_t)kt * H * 32, H);
     } else if (job < nJB + nJA) {
+      if (TC) return;                          // tensor-core dW2 jobs generate both operands
       const int j = job - nJB, nt = j / NP, kt0 = 2 * (j - nt * NP), kp = min(JA_ROWS, B);
       stage_block(st, R2, a.h2t + (size_t)nt * B * 32, kp);
       stage_block(st, R1, a.h1 + (size_t)kt0 * B * 32, kp);
@@ -837,6 +830,9 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       bulk_g2s(dst, src, 16384u, bar);
       bulk_g2s(dst + 16384u, src + (size_t)H * H, 16384u, bar);
     };
+    if (TC && cta >= nJB && cta < nJB + nJA) {     // dW2 job: all minibatch rows' inputs, transposed [D][B], under the row phase
+      for (int e = tid; e < B * D; e += NT) { const int m = e / D, i = e - m * D; R2[i * B + m] = ldcg(a.xg + e); }
+    }
     if (TC && cta < nJB && tid == 0) {
       jb_issue_a(cta / MT, 0, jb_g);
       if ((H >> 5) > 1) jb_issue_a(cta / MT, 1, jb_g + 1);
@@ -1118,6 +1114,128 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         TR(34);
         if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(a.barrier + CTR_JB + kt) : "memory");
         TR(16);
+      } else if (TC && job < nJB + nJA) {
+        // ---- tensor-core dW2 job: D[128 k][32 n] = sum_m h1[m][k] dh2[m][n]  (a tile of dW2^T), K = minibatch rows in chunks of 32.
+        // Both operands are GENERATED: A chunk = h1^T [128 k][32 m] = relu(x W1^T + b1) (thread = one k, 16 rows),
+        // B chunk = dh2^T [32 n][32 m] (thread = one n, 4 rows); db2 = row sums of the B operand (jobs of k-tile 0).
+        const int j = job - nJB, kt4 = j / NTL, nt = j - kt4 * NTL, k0 = kt4 * 128, n0 = nt * 32, NMC = B >> 5;
+        float* xall = R2;                                          // [D][B]
+        if (job != cta) {
+          __syncthreads();
+          for (int e = tid; e < B * D; e += NT) { const int m = e / D, i = e - m * D; xall[i * B + m] = ldcg(a.xg + e); }
+        }
+        const int r = tid & 127, half = tid >> 7;                  // A: hidden unit k0 + r, rows 16 half .. + 15 of a chunk
+        float w1r[MAXD];
+#pragma unroll
+        for (int i = 0; i < MAXD; ++i) w1r[i] = i < D ? ldcg(a.W1 + (size_t)(k0 + r) * D + i) : 0.f;
+        const float b1v = PS[(MAXO + 1) * PK + k0 + r];
+        const int nl = tid >> 3, c8 = tid & 7;                     // B: hidden unit n0 + nl, rows 4 c8 .. + 3 of a chunk
+        float whn[MAXO];
+#pragma unroll
+        for (int o = 0; o < MAXO; ++o) whn[o] = o < nout ? PS[o * PK + n0 + nl] : 0.f;
+        const float* h2col = a.h2t + (size_t)nt * B * 32 + nl;      // h2[m][n0 + nl] = h2col[m * 32]
+        float hq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hq[q] = ldcg(h2col + (size_t)(4 * c8 + q) * 32);
+        float b2acc = 0.f;
+        __syncthreads();                                            // xall complete
+        for (int mc = 0; mc < NMC; ++mc) {
+          const unsigned long long g = ja_g + mc;
+          const unsigned slot = (unsigned)(g % TC_NA);
+          if (g >= TC_NA) mbar_wait(tc_bar + 8u * (16u + slot), (unsigned)((g / TC_NA - 1) & 1));     // chunk g - 3 retired
+          const unsigned abuf = tc_base + slot * TC_A_BYTES, bbuf = tc_base + TC_NA * TC_A_BYTES + slot * TC_B_BYTES;
+          // A chunk
+          float hv[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) hv[jj] = 0.f;
+#pragma unroll
+          for (int i = 0; i < MAXD; ++i) {
+            if (i < D) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float4 x4 = *reinterpret_cast<const float4*>(&xall[i * B + mc * 32 + half * 16 + 4 * c]);
+                hv[4 * c] = fmaf(x4.x, w1r[i], hv[4 * c]); hv[4 * c + 1] = fmaf(x4.y, w1r[i], hv[4 * c + 1]);
+                hv[4 * c + 2] = fmaf(x4.z, w1r[i], hv[4 * c + 2]); hv[4 * c + 3] = fmaf(x4.w, w1r[i], hv[4 * c + 3]);
+              }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const unsigned off = tc_tile_off(r, half * 4 + c);
+            const float4 hi = make_float4(fmaxf(hv[4 * c] + b1v, 0.f), fmaxf(hv[4 * c + 1] + b1v, 0.f), fmaxf(hv[4 * c + 2] + b1v, 0.f), fmaxf(hv[4 * c + 3] + b1v, 0.f));
+            const float4 lo = make_float4(tf32_lo(hi.x), tf32_lo(hi.y), tf32_lo(hi.z), tf32_lo(hi.w));
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(abuf + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(abuf + 16384u + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+          }
+          // B chunk
+          {
+            float hc[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hc[q] = hq[q];
+            if (mc + 1 < NMC) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) hq[q] = ldcg(h2col + (size_t)((mc + 1) * 32 + 4 * c8 + q) * 32);
+            }
+            float dv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float* d = &dsm[(mc * 32 + 4 * c8 + q) * MAXO];
+              const float4 d0 = *reinterpret_cast<const float4*>(d), d1 = *reinterpret_cast<const float4*>(d + 4);
+              float t = d0.x * whn[0];
+              t = fmaf(d0.y, whn[1], t); t = fmaf(d0.z, whn[2], t); t = fmaf(d0.w, whn[3], t);
+              t = fmaf(d1.x, whn[4], t); t = fmaf(d1.y, whn[5], t); t = fmaf(d1.z, whn[6], t); t = fmaf(d1.w, whn[7], t);
+              dv[q] = hc[q] > 0.f ? t : 0.f;                        // same arithmetic as dh2_quad
+            }
+            b2acc += (dv[0] + dv[1]) + (dv[2] + dv[3]);
+            const unsigned off = tc_tile_off(nl, c8);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(bbuf + off), "f"(dv[0]), "f"(dv[1]), "f"(dv[2]), "f"(dv[3]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(bbuf + 4096u + off), "f"(tf32_lo(dv[0])), "f"(tf32_lo(dv[1])), "f"(tf32_lo(dv[2])), "f"(tf32_lo(dv[3])) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          __syncthreads();
+          if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const unsigned ko = 32u * jj;
+              tc_mma(tc_tmem, tc_desc(abuf + ko), tc_desc(bbuf + ko), TC_IDESC_N32, (mc > 0 || jj > 0) ? 1u : 0u);
+              tc_mma(tc_tmem, tc_desc(abuf + ko), tc_desc(bbuf + 4096u + ko), TC_IDESC_N32, 1u);
+              tc_mma(tc_tmem, tc_desc(abuf + 16384u + ko), tc_desc(bbuf + ko), TC_IDESC_N32, 1u);
+            }
+            tc_commit(tc_bar + 8u * (16u + slot));
+            if (mc == NMC - 1) tc_commit(tc_bar + 8u * 9u);
+          }
+        }
+        mbar_wait(tc_bar + 8u * 9u, tc_tiles & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        {
+          const int q = warp & 3, cb = (warp >> 2) * 16, kk = k0 + q * 32 + lane;
+          unsigned rr[16];
+          const unsigned taddr = tc_tmem + ((unsigned)(q * 32) << 16) + (unsigned)cb;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+              : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]),
+                "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float v = __uint_as_float(rr[i]);
+            a.gW2[(size_t)(n0 + cb + i) * H + kk] = v;              // lanes = consecutive k: 128-byte rows
+            sq = fmaf(v, v, sq);
+          }
+          if (kt4 == 0) {                                          // db2[n] = sum over all rows: fold the 8 row groups of hidden unit nl
+            float t = b2acc;
+            t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4);
+            if (c8 == 0) { a.gb2[n0 + nl] = t; sq = fmaf(t, t, sq); }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          __syncthreads();
+        }
+        ja_g += (unsigned long long)NMC;
+        tc_tiles += 1u;
+        TR(21);
       } else if (job < nJB + nJA) {
         // ---- a pair of dW2 tiles [n0.., k0..] = sum_m dh2[m, n] h1[m, k] sharing the dh2 panel; db2 = its row sums
         const int j = job - nJB;
