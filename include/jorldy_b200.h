@@ -91,6 +91,9 @@ JB_API int jb_linear_bwd_dx(const float* dy, const float* w, float* dx, int M, i
                             const float* relu_act, void* stream);
 JB_API int jb_linear_bwd_dw(const float* dy, const float* x, float* dw, float* db, int M, int in_f, int out_f,
                             void* stream);
+JB_API int
+jb_linear_bwd_dw_splitk(const float* dy, const float* x, float* dw, float* db, int M, int in_f, int out_f,
+                        float* workspace, int splits, void* stream);
 JB_API int jb_linear_io_fwd(const float* x, const float* w, const float* b, float* y, int M, int in_f, int out_f,
                             int relu, void* stream);
 JB_API int jb_linear_io_bwd_dx(const float* dy, const float* w, float* dx, int M, int in_f, int out_f,

@@ -105,8 +105,13 @@ class CNNHead:
             K = ci * k * k
             Mr = M * oh * ow
             col = net._buf(f"{tag}head.col{li}", (Mr, K))
-            C.jb_linear_bwd_dw(ptr(dy), ptr(col), ptr(net.g[f"head.{name}.weight"]), ptr(net.g[f"head.{name}.bias"]),
-                               Mr, K, co, s)
+            # conv weight gradients are [co, ci k k] = a few 32 x 32 tiles contracted over M * oh * ow rows: split the
+            # contraction over the grid (148 SMs) and fold the partials in a fixed order
+            tiles = ((K + 31) // 32) * ((co + 31) // 32)
+            splits = min(64, max(1, 296 // tiles), max(1, Mr // 512))
+            ws = net._buf(f"{tag}head.dwws{li}", (splits * (co * K + co),)) if splits > 1 else None
+            C.jb_linear_bwd_dw_splitk(ptr(dy), ptr(col), ptr(net.g[f"head.{name}.weight"]), ptr(net.g[f"head.{name}.bias"]),
+                                      Mr, K, co, ptr(ws), splits, s)
             if li == 0:
                 break
             dcol = net._buf(f"{tag}head.dcol{li}", (Mr, K))

@@ -46,6 +46,17 @@ gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, i
   float (*As)[BK][BM + PAD] = reinterpret_cast<float (*)[BK][BM + PAD]>(smem);
   float (*Bs)[BK][BN + PAD] = reinterpret_cast<float (*)[BK][BN + PAD]>(smem + 2 * BK * (BM + PAD));
 
+  // grid-level split-K (gridDim.z > 1): slice z contracts k in [z kc, (z + 1) kc) and writes a PARTIAL tile to
+  // C + z * M * ldc (and partial row sums to rowsum_a + z * M); splitk_reduce_kernel folds the slices in z order.
+  if (gridDim.z > 1) {
+    const int kc = ((K + (int)gridDim.z * BK - 1) / ((int)gridDim.z * BK)) * BK;
+    const int kz0 = (int)blockIdx.z * kc, kz1 = min(K, kz0 + kc);
+    A += A_KC ? (size_t)kz0 : (size_t)kz0 * lda;
+    B += B_KC ? (size_t)kz0 : (size_t)kz0 * ldb;
+    K = max(0, kz1 - kz0);
+    C += (size_t)blockIdx.z * M * ldc;
+    if (rowsum_a) rowsum_a += (size_t)blockIdx.z * M;
+  }
   const int tid = threadIdx.x;
   const int grp = tid / (TX * TY);
   const int t = tid % (TX * TY);
@@ -441,6 +452,34 @@ JB_API int jb_linear_bwd_dw(const float* dy, const float* x, float* dw, float* d
 }
 
 // ---- NoisyNet-shaped wrappers (weight [in,out], y = x W + b; network/utils.py:84) ---------------
+// out[i] = sum_z part[z * n + i] in ascending z (fixed order: deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int S, long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = part[i];
+  for (int z = 1; z < S; ++z) v += part[(size_t)z * n + i];
+  out[i] = v;
+}
+
+// weight gradient with a grid-level split of the contraction (the conv layers' dW: tiny [out, in] outputs, K = batch x
+// positions in the 10^4 .. 10^5 range, where the plain tiling is 8-32 CTAs).  workspace: >= splits * (out_f * in_f + out_f)
+// floats; partials are folded in split order.  splits <= 1 falls back to jb_linear_bwd_dw.
+JB_API int jb_linear_bwd_dw_splitk(const float* dy, const float* x, float* dw, float* db, int M, int in_f, int out_f,
+                                   float* workspace, int splits, void* stream) {
+  if (!dy || !x || !dw || M <= 0 || in_f <= 0 || out_f <= 0) return JB_ERR_INVALID;
+  if (splits <= 1 || !workspace) return jb_linear_bwd_dw(dy, x, dw, db, M, in_f, out_f, stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  float* part_w = workspace;
+  float* part_b = workspace + (size_t)splits * out_f * in_f;
+  dim3 grid(jb_div_up(in_f, 32), jb_div_up(out_f, 32), splits);
+  gemm_kernel<32, 32, 32, 4, 4, 4, false, false><<<grid, 256, 0, s>>>(dy, out_f, x, in_f, part_w, in_f, out_f, in_f, M, nullptr, 0,
+                                                                     nullptr, 0, db ? part_b : nullptr, 0);
+  const long long n = (long long)out_f * in_f;
+  splitk_reduce_kernel<<<jb_div_up(n, 256), 256, 0, s>>>(part_w, splits, n, dw);
+  if (db) splitk_reduce_kernel<<<jb_div_up(out_f, 256), 256, 0, s>>>(part_b, splits, out_f, db);
+  return jb_check_launch();
+}
+
 JB_API int jb_linear_io_fwd(const float* x, const float* w, const float* b, float* y, int M, int in_f, int out_f,
                             int relu, void* stream) {
   return jb_gemm(x, in_f, 1, w, out_f, 0, y, out_f, M, out_f, in_f, b, relu, nullptr, 0, nullptr, 0, stream);

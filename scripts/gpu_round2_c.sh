@@ -2,7 +2,7 @@
 # 1-GPU call: tensor-core forward phase of the persistent kernel: PPO tests, timeline, bench, per-kernel ncu list
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_ppo_gpu.py tests/test_collect_gpu.py -q > gpurun_out/r02_pytest_c.txt 2>&1; echo "pytest rc=$?"
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_c.txt 2>&1; echo "pytest rc=$?"
 tail -40 gpurun_out/r02_pytest_c.txt | cut -c1-300
 timeout 200 python scripts/perf_trace.py > gpurun_out/r02_trace_tc.txt 2>&1; echo "trace rc=$?"; head -45 gpurun_out/r02_trace_tc.txt
 JB_FUSED_NO_TC=1 timeout 200 python scripts/perf_trace.py > gpurun_out/r02_trace_ffma.txt 2>&1; head -3 gpurun_out/r02_trace_ffma.txt
