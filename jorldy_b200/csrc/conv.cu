@@ -30,6 +30,22 @@ __global__ void im2col_u8_nchw_kernel(const uint8_t* __restrict__ x, int B, int 
   }
 }
 
+// Same, four consecutive kx per thread (KW % 4 == 0, S % 4 == 0, W % 4 == 0: the 8x8 stride-4 first layer): one 4-byte
+// load of the frame row and one 16-byte store of the column row per thread, 32-bit index arithmetic.
+__global__ void im2col_u8_nchw_vec4_kernel(const uint8_t* __restrict__ x, int B, int C, int H, int W, int KH, int KW, int S,
+                                           int OH, int OW, float* __restrict__ col) {
+  const int K4 = (C * KH * KW) >> 2, KW4 = KW >> 2;
+  const long long total = (long long)B * OH * OW * K4;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k4 = (int)(e % K4);
+    const int m = (int)(e / K4);
+    const int ox = m % OW, t = m / OW, oy = t % OH, b = t / OH;
+    const int kx4 = k4 % KW4, t2 = k4 / KW4, ky = t2 % KH, c = t2 / KH;
+    const uchar4 v = *reinterpret_cast<const uchar4*>(x + (((size_t)b * C + c) * H + oy * S + ky) * W + ox * S + 4 * kx4);
+    reinterpret_cast<float4*>(col)[e] = make_float4((float)v.x / 255.0f, (float)v.y / 255.0f, (float)v.z / 255.0f, (float)v.w / 255.0f);
+  }
+}
+
 // x: [B, H, W, C] f32 (NHWC)  ->  col [B*OH*OW, C*KH*KW]
 __global__ void im2col_nhwc_kernel(const float* __restrict__ x, int B, int C, int H, int W, int KH, int KW, int S,
                                    int OH, int OW, float* __restrict__ col) {
@@ -99,7 +115,11 @@ static int conv_grid(long long total) { return jb_grid_for(total, 256 * 4, 8); }
 JB_API int jb_im2col_u8(const uint8_t* x, int B, int C, int H, int W, int KH, int KW, int S, float* col, void* stream) {
   if (!x || !col || B <= 0 || C <= 0 || H < KH || W < KW || S <= 0) return JB_ERR_INVALID;
   const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
-  im2col_u8_nchw_kernel<<<conv_grid((long long)B * OH * OW * C * KH * KW), 256, 0, (cudaStream_t)stream>>>(x, B, C, H, W, KH, KW, S, OH, OW, col);
+  const long long total = (long long)B * OH * OW * C * KH * KW;
+  if (KW % 4 == 0 && S % 4 == 0 && W % 4 == 0 && (((uintptr_t)x | (uintptr_t)col) & 15) == 0 && (long long)B * OH * OW < (1ll << 31))
+    im2col_u8_nchw_vec4_kernel<<<conv_grid(total / 4), 256, 0, (cudaStream_t)stream>>>(x, B, C, H, W, KH, KW, S, OH, OW, col);
+  else
+    im2col_u8_nchw_kernel<<<conv_grid(total), 256, 0, (cudaStream_t)stream>>>(x, B, C, H, W, KH, KW, S, OH, OW, col);
   return jb_check_launch();
 }
 
