@@ -61,6 +61,13 @@ jb_env_synth_step(float* obs, int32_t* elapsed, int64_t* episode, int64_t* tcoun
                   float* done, float* stats, int auto_reset, int max_steps, float p_done, uint64_t seed,
                   uint64_t stream_base, int n, int D, int A, void* stream);
 
+/* Replay ring rows (jorldy/core/buffer/replay_buffer.py:16-31, base.py:42-56 stack_transition): a field is a
+ * [capacity, row_bytes] byte matrix; store scatters n batch rows to ring positions, gather collects a minibatch. */
+JB_API int
+jb_replay_store(void* ring, const void* batch, const int64_t* pos, int n, long long row_bytes, void* stream);
+JB_API int
+jb_replay_gather(const void* ring, const int64_t* idx, int n, long long row_bytes, void* batch, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * PER sum-tree — jorldy/core/buffer/per_buffer.py:19-101.  tree is f64[2*capacity-1].
  * ------------------------------------------------------------------------------------------- */

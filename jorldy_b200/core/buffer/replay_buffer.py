@@ -3,7 +3,7 @@
 The reference keeps a numpy array of python dicts and stacks B of them per sample; here every
 transition field is one device tensor [capacity, ...] (structure of arrays, allocated on the
 first store from the transition's own shapes), `store` is one host->device copy per field +
-an index_copy into the ring, and `sample` is a device gather.  Integer bookkeeping
+a row scatter into the ring and `sample` a row gather (csrc/replay.cu: jb_replay_store / jb_replay_gather).  Integer bookkeeping
 (`buffer_index`, `buffer_counter`, `size`) matches the reference exactly and lives on the host.
 
 dtypes in HBM: uint8 observations stay uint8 (the learner casts, base.py:61-73); float64 fields
@@ -14,7 +14,7 @@ bool -> uint8; int64 kept.  `sample()` returns numpy arrays with the dtypes the 
 import numpy as np
 import torch
 
-from ..dev import require_cuda
+from ..dev import C, ptr, require_cuda, stream_ptr
 from .base import BaseBuffer
 
 _STORE_DTYPE = {np.dtype("float64"): torch.float32, np.dtype("float32"): torch.float32,
@@ -82,12 +82,32 @@ class ReplayBuffer(BaseBuffer):
         for key, dst in self.fields.items():
             if isinstance(dst, list):
                 for i, d in enumerate(dst):
-                    src = self._cat([t[key][i] for t in transitions], d.dtype, self.device)
-                    d.index_copy_(0, pos[keep], src[keep])
+                    self._scatter(d, self._cat([t[key][i] for t in transitions], d.dtype, self.device)[keep], pos[keep])
             else:
-                src = self._cat([t[key] for t in transitions], dst.dtype, self.device)
-                dst.index_copy_(0, pos[keep], src[keep])
+                self._scatter(dst, self._cat([t[key] for t in transitions], dst.dtype, self.device)[keep], pos[keep])
         return n
+
+    _MAX_ROWS = 32768          # rows per launch (grid.y)
+
+    @staticmethod
+    def _row_bytes(t):
+        return t[0].numel() * t.element_size() if t.dim() > 1 else t.element_size()
+
+    def _scatter(self, ring, rows, pos):
+        rows = rows.contiguous().view(rows.shape[0], -1) if rows.dim() > 1 else rows.contiguous()
+        assert rows.dtype == ring.dtype and self._row_bytes(rows) == self._row_bytes(ring), "transition field changed shape"
+        rb, n = self._row_bytes(ring), rows.shape[0]
+        for off in range(0, n, self._MAX_ROWS):
+            m = min(self._MAX_ROWS, n - off)
+            C.jb_replay_store(ptr(ring), ptr(rows[off:off + m]), ptr(pos[off:off + m]), m, rb, stream_ptr())
+
+    def _gather(self, ring, idx):
+        out = torch.empty((idx.shape[0],) + tuple(ring.shape[1:]), dtype=ring.dtype, device=ring.device)
+        rb, n = self._row_bytes(ring), idx.shape[0]
+        for off in range(0, n, self._MAX_ROWS):
+            m = min(self._MAX_ROWS, n - off)
+            C.jb_replay_gather(ptr(ring), ptr(idx[off:off + m]), m, rb, ptr(out[off:off + m]), stream_ptr())
+        return out
 
     def store(self, transitions):
         if self.first_store:
@@ -101,8 +121,9 @@ class ReplayBuffer(BaseBuffer):
     def gather_device(self, idx):
         """idx: int64 device tensor of ring positions -> dict of device tensors (stored dtypes)."""
         out = {}
+        idx = idx.to(torch.int64).contiguous()
         for key, src in self.fields.items():
-            out[key] = [s.index_select(0, idx) for s in src] if isinstance(src, list) else src.index_select(0, idx)
+            out[key] = [self._gather(s, idx) for s in src] if isinstance(src, list) else self._gather(src, idx)
         return out
 
     def _to_numpy(self, dev_dict):
