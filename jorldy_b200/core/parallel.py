@@ -4,9 +4,9 @@ backward and the clip+Adam launch.  Collection, GAE and advanta
 are per-env-row and never cross ranks.  The reference has no counterpart (single learner; ray
 actors only collect: manager/distributed_manager.py:7-65).
 
-Known, documented deviation at world_size > 1: `critic_loss = max(mean1, mean2)` (ppo.py:151-154)
-is evaluated per rank on its local minibatch shard (a 2-float all-reduce before backward would
-make it global; at B=256/rank the two means are equal in all but the clipped-value regime).
+`critic_loss = max(mean1, mean2)` (ppo.py:151-154): the in-kernel exchange makes the two means GLOBAL (the ranks swap
+their row sums during the row phase, csrc/ppo_fused.cu); only the NCCL fallback path (symmetric memory unavailable,
+JB_NO_P2P=1, CNN heads) still evaluates the max per rank on its local minibatch shard.
 """
 import torch
 import torch.distributed as dist
@@ -22,6 +22,9 @@ def _try_p2p(agent, world_size):
     INSIDE the kernel instead of 6144 NCCL calls per learn().
     Falls back silently (agent.p2p = None -> CUDA graphs + NCCL) when symmetric memory is unavailable."""
     agent.p2p = None
+    import os
+    if os.environ.get("JB_NO_P2P", "0") == "1":          # operator override: CUDA graphs + ncclAllReduce instead
+        return
     net = getattr(agent, "network", None)
     # (these conditions are identical on every rank, so the early return is itself a collective decision)
     if net is None or not net.flat.is_cuda or dist.get_backend() != "nccl" or world_size > 8 or type(agent).__name__ != "PPO":

