@@ -370,7 +370,7 @@ __device__ __forceinline__ float tf32_lo(float x) {
 }
 constexpr int TC_A_BYTES = 2 * 128 * 128;        // one A chunk: hi | lo, each [128 rows][32 k] fp32 = 16 KB
 constexpr int TC_B_BYTES = 2 * 32 * 128;         // one B chunk: hi | lo, each [32 rows][32 k] fp32 = 4 KB
-constexpr int TC_NA = 3, TC_NB = 6;              // ring depths: A chunks are generated, B chunks stream in 5 ahead
+constexpr int TC_NA = 3, TC_NB = 5;              // ring depths: A chunks are generated, B chunks stream in 4 ahead (+ 8 KB: x tile)
 constexpr int TC_BAR_WORD = 1664;                // s_small word offset of the tensor-core mbarriers (32 x 8 bytes)
 constexpr int TC_TMEM_WORD = 1660;               // s_small word that receives the TMEM base address
 constexpr int TC_NBAR = 24;                      // [0..9] forward, [10..15] dh1 jobs, [16..23] dW2 jobs
@@ -381,8 +381,9 @@ __device__ long long g_trace[256 * 48];
 
 struct HeadTab { const float* w[MAXO]; const float* b[MAXO]; float* gw[MAXO]; float* gb[MAXO]; };
 
-// TC: tensor-core forward phase (B % 128 == 0); NA: compile-time bound on the action count (row maths loop bound)
-template <bool TC, int NA>
+// TC: tensor-core phases (B % 128 == 0, H % 128 == 0); NA / ND: compile-time bounds on the action count / the input
+// dimension (loop bounds of the row maths / of the operand generators: a D = 4 net must not pay for 16 predicated slots)
+template <bool TC, int NA, int ND>
 __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats, int flags /* debug: bit 8 = trace */) {
   extern __shared__ __align__(16) float smem[];
   float* s_small = smem;                       // SMALL_FLOATS
@@ -533,14 +534,14 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
   gather_rows();
   // state rows of this CTA's first P1 tile of step 0 (later steps: gathered under the Adam phase)
   bool xs_ready = false;
-  float xpre[MAXD];                              // TC: this thread's state row (row tid & 127 of the CTA's first tile)
+  float xpre[ND];                                // TC: this thread's state row (row tid & 127 of the CTA's first tile)
   int xpre_idx = 0;
 #pragma unroll
-  for (int i = 0; i < MAXD; ++i) xpre[i] = 0.f;
+  for (int i = 0; i < ND; ++i) xpre[i] = 0.f;
   if (TC && cta < nJ1) {
     xpre_idx = a.perm[cursor0 * (long long)B + (cta / NTL) * 128 + (tid & 127)];
 #pragma unroll
-    for (int i = 0; i < MAXD; ++i) if (i < D) xpre[i] = a.state[(size_t)xpre_idx * D + i];
+    for (int i = 0; i < ND; ++i) if (i < D) xpre[i] = a.state[(size_t)xpre_idx * D + i];
     xs_ready = true;
   }
   if (!TC && cta < nJ1) {
@@ -600,21 +601,30 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         };
         if (tid == 0)
           for (int kc = 0; kc < min(TC_NB - 1, NKC); ++kc) issue_b(kc, tc_g + kc);
-        float xr[MAXD];
+        float xr[ND];
         int xidx;
         if (job == cta && xs_ready) {
           xidx = xpre_idx;
 #pragma unroll
-          for (int i = 0; i < MAXD; ++i) xr[i] = xpre[i];
+          for (int i = 0; i < ND; ++i) xr[i] = xpre[i];
         } else {
           xidx = a.perm[(cursor0 + s) * (long long)B + m0 + r];
 #pragma unroll
-          for (int i = 0; i < MAXD; ++i) xr[i] = i < D ? a.state[(size_t)xidx * D + i] : 0.f;
+          for (int i = 0; i < ND; ++i) xr[i] = i < D ? a.state[(size_t)xidx * D + i] : 0.f;
         }
         if (nt == 0 && half == 0) {
           a.cur_idx[m0 + r] = xidx;
           for (int i = 0; i < D; ++i) a.xg[(size_t)(m0 + r) * D + i] = xr[i];
         }
+        // the tile's 128 input rows, transposed [ND][128], in the spare 8 KB behind the operand rings: the generator
+        // below reads them as broadcast float4 (4 rows of one input feature)
+        float* xt = tcp + ((TC_NA * TC_A_BYTES + TC_NB * TC_B_BYTES) >> 2);
+        __syncthreads();                                          // previous tile's generators are done with xt
+        if (half == 0) {
+#pragma unroll
+          for (int i = 0; i < ND; ++i) xt[i * 128 + r] = xr[i];
+        }
+        __syncthreads();
         const float* W1s = R2;
         const float* b1s = PS + (MAXO + 1) * PK;
         TR(1);
@@ -622,23 +632,34 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           const unsigned long long g = tc_g + kc;
           const unsigned abuf = tc_base + (unsigned)(g % TC_NA) * TC_A_BYTES;
           if (g >= TC_NA) mbar_wait(tc_bar + 8u * (unsigned)(g % TC_NA), (unsigned)((g / TC_NA - 1) & 1));   // chunk g - 3 retired
+          // generator: lane = hidden unit 32 kc + lane (its W1 row in registers), warp = rows 16 warp .. + 15
+          const int k = kc * 32 + lane;
+          float w1k[ND];
+#pragma unroll
+          for (int i = 0; i < ND; ++i) w1k[i] = i < D ? W1s[k * D + i] : 0.f;
+          const float b1k = b1s[k];
           float hv[16];
-          const int kb = kc * 32 + half * 16;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float h = 0.f;
+          for (int j = 0; j < 16; ++j) hv[j] = 0.f;
 #pragma unroll
-            for (int i = 0; i < MAXD; ++i) if (i < D) h = fmaf(xr[i], W1s[(kb + j) * D + i], h);
-            hv[j] = fmaxf(h + b1s[kb + j], 0.f);
+          for (int i = 0; i < ND; ++i) {
+            if (i < D) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float4 x4 = *reinterpret_cast<const float4*>(&xt[i * 128 + warp * 16 + 4 * c]);
+                hv[4 * c] = fmaf(x4.x, w1k[i], hv[4 * c]); hv[4 * c + 1] = fmaf(x4.y, w1k[i], hv[4 * c + 1]);
+                hv[4 * c + 2] = fmaf(x4.z, w1k[i], hv[4 * c + 2]); hv[4 * c + 3] = fmaf(x4.w, w1k[i], hv[4 * c + 3]);
+              }
+            }
           }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const unsigned off = tc_tile_off(r, half * 4 + c);
-            const float4 hi = make_float4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
-            const float4 lo = make_float4(tf32_lo(hi.x), tf32_lo(hi.y), tf32_lo(hi.z), tf32_lo(hi.w));
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(abuf + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(abuf + 16384u + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-            if (nt == 0) *reinterpret_cast<float4*>(a.h1 + ((size_t)kc * B + m0 + r) * 32 + half * 16 + 4 * c) = hi;   // tiled [H/32][B][32]
+          for (int j = 0; j < 16; ++j) {
+            const int row = warp * 16 + j;
+            const float hi = fmaxf(hv[j] + b1k, 0.f);
+            const unsigned off = tc_tile_off(row, lane >> 2) + ((unsigned)(lane & 3) << 2);
+            asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(abuf + off), "f"(hi) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(abuf + 16384u + off), "f"(tf32_lo(hi)) : "memory");
+            if (nt == 0) a.h1[((size_t)kc * B + m0 + row) * 32 + lane] = hi;                  // tiled [H/32][B][32]
           }
           asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> async proxy (UMMA reads)
           __syncthreads();
@@ -1013,36 +1034,36 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
               : "memory");
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
           // h1[m][kin] > 0 ?  (same arithmetic as the forward phase: fma chain over the inputs, then + b1)
-          float w1r[MAXD];
+          float w1r[ND];
 #pragma unroll
-          for (int i = 0; i < MAXD; ++i) w1r[i] = i < D ? ldcg(a.W1 + (size_t)kin * D + i) : 0.f;
+          for (int i = 0; i < ND; ++i) w1r[i] = i < D ? ldcg(a.W1 + (size_t)kin * D + i) : 0.f;
           const float b1v = PS[(MAXO + 1) * PK + kin];
-          float wacc[MAXD + 1];
+          float wacc[ND + 1];
 #pragma unroll
-          for (int i = 0; i <= MAXD; ++i) wacc[i] = 0.f;
+          for (int i = 0; i <= ND; ++i) wacc[i] = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int ml2 = cb + j;
             float h = 0.f;
 #pragma unroll
-            for (int i = 0; i < MAXD; ++i) if (i < D) h = fmaf(xs[i * 32 + ml2], w1r[i], h);
+            for (int i = 0; i < ND; ++i) if (i < D) h = fmaf(xs[i * 32 + ml2], w1r[i], h);
             const float dvv = (h + b1v > 0.f) ? __uint_as_float(rr[j]) : 0.f;
 #pragma unroll
-            for (int i = 0; i < MAXD; ++i) if (i < D) wacc[i] = fmaf(dvv, xs[i * 32 + ml2], wacc[i]);
-            wacc[MAXD] += dvv;
+            for (int i = 0; i < ND; ++i) if (i < D) wacc[i] = fmaf(dvv, xs[i * 32 + ml2], wacc[i]);
+            wacc[ND] += dvv;
           }
           float* sc = tcp + (size_t)(q * 32 + lane) * (MAXD + 1);       // [128 k][MAXD + 1] scratch in ring slot 0
           if (warp >= 4) {
 #pragma unroll
-            for (int i = 0; i <= MAXD; ++i) if (i < D || i == MAXD) sc[i] = wacc[i];
+            for (int i = 0; i <= ND; ++i) if (i < D || i == ND) sc[i < D ? i : MAXD] = wacc[i];
           }
           asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
           __syncthreads();
           if (warp < 4) {
             float* dstw = a.w1p + ((size_t)mt * H + kin) * (D + 1);
 #pragma unroll
-            for (int i = 0; i < MAXD; ++i) if (i < D) dstw[i] = wacc[i] + sc[i];
-            dstw[D] = wacc[MAXD] + sc[MAXD];
+            for (int i = 0; i < ND; ++i) if (i < D) dstw[i] = wacc[i] + sc[i];
+            dstw[D] = wacc[ND] + sc[MAXD];
           }
           __syncthreads();
         }
@@ -1050,7 +1071,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         jb_g += (unsigned long long)NKC;
         tc_tiles += 1u;
         TR(16);
-      } else if (job < nJB) {
+      } else if (!TC && job < nJB) {
         // ---- dh1 tile = ((dout Wh) * relu'(h2)) W2, masked by relu'(h1); partial dW1 / db1 ---------------
         const int mt = job / NTL, kt = job - mt * NTL;
         const int m0 = mt * 32, k0 = kt * 32;
@@ -1125,9 +1146,9 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           for (int e = tid; e < B * D; e += NT) { const int m = e / D, i = e - m * D; xall[i * B + m] = ldcg(a.xg + e); }
         }
         const int r = tid & 127, half = tid >> 7;                  // A: hidden unit k0 + r, rows 16 half .. + 15 of a chunk
-        float w1r[MAXD];
+        float w1r[ND];
 #pragma unroll
-        for (int i = 0; i < MAXD; ++i) w1r[i] = i < D ? ldcg(a.W1 + (size_t)(k0 + r) * D + i) : 0.f;
+        for (int i = 0; i < ND; ++i) w1r[i] = i < D ? ldcg(a.W1 + (size_t)(k0 + r) * D + i) : 0.f;
         const float b1v = PS[(MAXO + 1) * PK + k0 + r];
         const int nl = tid >> 3, c8 = tid & 7;                     // B: hidden unit n0 + nl, rows 4 c8 .. + 3 of a chunk
         float whn[MAXO];
@@ -1149,7 +1170,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) hv[jj] = 0.f;
 #pragma unroll
-          for (int i = 0; i < MAXD; ++i) {
+          for (int i = 0; i < ND; ++i) {
             if (i < D) {
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
@@ -1236,7 +1257,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         ja_g += (unsigned long long)NMC;
         tc_tiles += 1u;
         TR(21);
-      } else if (job < nJB + nJA) {
+      } else if (!TC && job < nJB + nJA) {
         // ---- a pair of dW2 tiles [n0.., k0..] = sum_m dh2[m, n] h1[m, k] sharing the dh2 panel; db2 = its row sums
         const int j = job - nJB;
         const int nt = j / NP, kt0 = 2 * (j - nt * NP);
@@ -1470,7 +1491,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         if (has_next) {
           xpre_idx = next_r;
 #pragma unroll
-          for (int i = 0; i < MAXD; ++i) if (i < D) xpre[i] = a.state[(size_t)next_r * D + i];
+          for (int i = 0; i < ND; ++i) if (i < D) xpre[i] = a.state[(size_t)next_r * D + i];
         }
       } else if (has_next) {
 #pragma unroll
@@ -1556,21 +1577,23 @@ static int dsm_floats_for(int B) { return B * MAXO; }
 static size_t fused_smem(int B) { return sizeof(float) * (size_t)(SMALL_FLOATS + dsm_floats_for(B) + 2 * RED_FLOATS + R2_FLOATS + PS_FLOATS); }
 
 // Largest grid the cooperative launch can keep co-resident (one CTA per SM on B200) for minibatch size B.
-static const void* fused_fn(bool tc, int A) {
-  const int na = A <= 2 ? 0 : (A <= 4 ? 1 : 2);
-  static const void* const tab[2][3] = {
-      {(const void*)ppo_epoch_kernel<false, 2>, (const void*)ppo_epoch_kernel<false, 4>, (const void*)ppo_epoch_kernel<false, 8>},
-      {(const void*)ppo_epoch_kernel<true, 2>, (const void*)ppo_epoch_kernel<true, 4>, (const void*)ppo_epoch_kernel<true, 8>}};
-  return tab[tc ? 1 : 0][na];
+static const void* fused_fn(bool tc, int A, int D) {
+  const int na = A <= 2 ? 0 : (A <= 4 ? 1 : 2), nd = D <= 4 ? 0 : 1;
+  // the FFMA instantiation keeps its round-1 generators (MAXD-strided tiles): one ND
+  static const void* const tab[3][3] = {
+      {(const void*)ppo_epoch_kernel<false, 2, 16>, (const void*)ppo_epoch_kernel<false, 4, 16>, (const void*)ppo_epoch_kernel<false, 8, 16>},
+      {(const void*)ppo_epoch_kernel<true, 2, 4>, (const void*)ppo_epoch_kernel<true, 4, 4>, (const void*)ppo_epoch_kernel<true, 8, 4>},
+      {(const void*)ppo_epoch_kernel<true, 2, 16>, (const void*)ppo_epoch_kernel<true, 4, 16>, (const void*)ppo_epoch_kernel<true, 8, 16>}};
+  return tab[tc ? 1 + nd : 0][na];
 }
 
-static int fused_max_ctas(int B, bool tc = false, int A = 8) {
+static int fused_max_ctas(int B, bool tc = false, int A = 8, int D = 16) {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t smem = fused_smem(B);
   if (smem > 227 * 1024) return 0;
-  const void* fn = fused_fn(tc, A);
+  const void* fn = fused_fn(tc, A, D);
   cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT, smem);
   return sms * (per_sm > 0 ? 1 : 0);
@@ -1598,7 +1621,7 @@ JB_API int jb_ppo_fused_run(const void* host_args, void* stream) {
   // tensor-core forward phase: 128-row tiles (B % 128 == 0) and the W2 image workspace; JB_FUSED_NO_TC=1 forces FFMA tiles
   bool tc = a.B % 128 == 0 && a.H % 128 == 0 && a.W2img != nullptr && a.W2Timg != nullptr;
   if (const char* e = getenv("JB_FUSED_NO_TC")) tc = tc && atoi(e) == 0;
-  int ctas = fused_max_ctas(a.B, tc, a.A);
+  int ctas = fused_max_ctas(a.B, tc, a.A, a.D);
   if (ctas <= 0) return JB_ERR_INVALID;
   if (ctas > NT) ctas = NT;
   if (a.world < 1 || a.world > 8 || a.rank < 0 || a.rank >= a.world) return JB_ERR_INVALID;
@@ -1615,7 +1638,7 @@ JB_API int jb_ppo_fused_run(const void* host_args, void* stream) {
   int flags = 0;
   if (const char* e = getenv("JB_FUSED_SKIP")) flags = atoi(e);     // bit 8: record the timing trace
   void* kargs[] = {&a, &dsm_floats, &flags};
-  cudaError_t e = cudaLaunchCooperativeKernel(const_cast<void*>(fused_fn(tc, a.A)), dim3(ctas), dim3(NT), kargs, smem, s);
+  cudaError_t e = cudaLaunchCooperativeKernel(const_cast<void*>(fused_fn(tc, a.A, a.D)), dim3(ctas), dim3(NT), kargs, smem, s);
   if (e != cudaSuccess) { cudaGetLastError(); return JB_ERR_CUDA; }
   return JB_OK;
 }
