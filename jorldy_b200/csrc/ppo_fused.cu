@@ -1618,9 +1618,13 @@ JB_API int jb_ppo_fused_run(const void* host_args, void* stream) {
   if (a.B <= 0 || a.B % 32 || a.B > MAX_B || a.H <= 0 || a.H % 32 || a.H > PK || a.D <= 0 || a.D > MAXD || a.nout <= 0 ||
       a.nout > MAXO || a.A <= 0 || a.A > jbppo::MAX_A || a.n_steps <= 0 || a.P4 <= 0)
     return JB_ERR_INVALID;
-  // tensor-core forward phase: 128-row tiles (B % 128 == 0) and the W2 image workspace; JB_FUSED_NO_TC=1 forces FFMA tiles
-  bool tc = a.B % 128 == 0 && a.H % 128 == 0 && a.W2img != nullptr && a.W2Timg != nullptr;
-  if (const char* e = getenv("JB_FUSED_NO_TC")) tc = tc && atoi(e) == 0;
+  // Tensor-core instantiation (3xTF32 tcgen05 for the three dense products): needs 128-row tiles (B % 128 == 0,
+  // H % 128 == 0) and the W2 image workspaces.  It is parity-green but, as measured in round 2, SLOWER than the FFMA tiles
+  // at the reference minibatch (with 128-row UMMA tiles only 32-64 CTAs work and each regenerates a 4x
+  // larger operand panel on the CUDA cores, which is instruction-issue bound), so it is opt-in: JB_FUSED_TC=1.
+  bool tc = false;
+  if (const char* e = getenv("JB_FUSED_TC")) tc = atoi(e) != 0;
+  tc = tc && a.B % 128 == 0 && a.H % 128 == 0 && a.W2img != nullptr && a.W2Timg != nullptr;
   int ctas = fused_max_ctas(a.B, tc, a.A, a.D);
   if (ctas <= 0) return JB_ERR_INVALID;
   if (ctas > NT) ctas = NT;

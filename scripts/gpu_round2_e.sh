@@ -6,8 +6,8 @@ mkdir -p gpurun_out
 O=gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > $O/r02_pytest.txt 2>&1; echo "pytest rc=$?"
 tail -25 $O/r02_pytest.txt | cut -c1-400
-timeout 200 python scripts/perf_trace.py > $O/r02_trace_tc.txt 2>&1; echo "trace rc=$?"; head -42 $O/r02_trace_tc.txt
-JB_FUSED_NO_TC=1 timeout 200 python scripts/perf_trace.py > $O/r02_trace_ffma.txt 2>&1; head -2 $O/r02_trace_ffma.txt
+JB_FUSED_TC=1 timeout 200 python scripts/perf_trace.py > $O/r02_trace_tc.txt 2>&1; echo "trace rc=$?"; head -42 $O/r02_trace_tc.txt
+JB_FUSED_TC=0 timeout 200 python scripts/perf_trace.py > $O/r02_trace_ffma.txt 2>&1; head -2 $O/r02_trace_ffma.txt
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > $O/r02_clocks_bench.csv &
 SMI=$!
 timeout 900 python bench.py --steps 20 --warmup 5 > $O/r02_bench_n1.json 2> $O/r02_bench_n1.err; echo "bench rc=$?"

@@ -62,12 +62,22 @@ def test_ppo_learn_matches_reference_golden(name, use_graph, monkeypatch):
     check_against_golden(gold, params_after, res, pre, rtol=1e-4, atol=0.1 * case["lr"], stat_tol=2e-4)
 
 
+@pytest.fixture(params=["ffma", "tcgen05"])
+def tile_engine(request, monkeypatch):
+    """Both instantiations of the persistent kernel: fp32 FFMA tiles (default) and the 3xTF32 tcgen05 tiles (JB_FUSED_TC=1,
+    taken when B % 128 == 0 and H % 128 == 0, else the launcher keeps the FFMA tiles)."""
+    monkeypatch.setenv("JB_FUSED_TC", "1" if request.param == "tcgen05" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("name", list(G.PPO_CASES.keys()))
-def test_ppo_fused_kernel_matches_reference_golden(name):
+def test_ppo_fused_kernel_matches_reference_golden(name, tile_engine):
     """Persistent cooperative minibatch-loop kernel (csrc/ppo_fused.cu) against the same goldens."""
     case = G.PPO_CASES[name]
     if case["batch_size"] % 32:
         pytest.skip("fused kernel needs B % 32 == 0 (host falls back to the multi-launch path)")
+    if tile_engine == "tcgen05" and (case["batch_size"] % 128 or case["H"] % 128):
+        pytest.skip("tensor-core tiles need B % 128 == 0 and H % 128 == 0")
     agent, res, _ = _run_cuda(case, False, use_fused=True)
     assert agent._fused, "fused path was not taken"
     gold = load_golden(name)
@@ -75,7 +85,7 @@ def test_ppo_fused_kernel_matches_reference_golden(name):
     check_against_golden(gold, params_after, res, None, rtol=1e-4, atol=0.1 * case["lr"], stat_tol=2e-4)
 
 
-def test_ppo_fused_equals_multilaunch_path():
+def test_ppo_fused_equals_multilaunch_path(tile_engine):
     """Same inputs through the fused kernel and the 13-launch path: parameters agree to fp32 round-off
     (the two paths share the row math and the Adam formula; only summation orders differ)."""
     case = G.PPO_CASES["ppo_discrete_h512"]
@@ -102,7 +112,7 @@ _FUSED_SHAPES = {
 
 
 @pytest.mark.parametrize("name", list(_FUSED_SHAPES.keys()))
-def test_ppo_fused_generic_shapes_equal_multilaunch(name):
+def test_ppo_fused_generic_shapes_equal_multilaunch(name, tile_engine):
     case = dict(lr=2.5e-4, gamma=0.99, lam=0.95, eps_clip=0.1, vf_coef=1.0, ent_coef=0.01, clip_grad_norm=1.0,
                 standardize=True, **_FUSED_SHAPES[name])
     a1, r1, _ = _run_cuda(case, False, use_fused=True)
@@ -141,7 +151,7 @@ def test_rebind_grad_keeps_both_paths_working():
         check_against_golden(gold, params_after, res, None, rtol=1e-4, atol=0.1 * case["lr"], stat_tol=2e-4)
 
 
-def test_ppo_fused_is_bit_reproducible():
+def test_ppo_fused_is_bit_reproducible(tile_engine):
     """Static job maps + fixed-order reductions: two runs give identical bits."""
     case = G.PPO_CASES["ppo_discrete_h512"]
     a1, _, _ = _run_cuda(case, False, use_fused=True)
