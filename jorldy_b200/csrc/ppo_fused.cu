@@ -772,8 +772,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           float h[16];
 #pragma unroll
           for (int r = 0; r < 16; ++r) h[r] = 0.f;
-#pragma unroll 1
-          for (int i = 0; i < D; ++i) {
+          auto feature = [&](int i) {
             const float w = W1s[k * D + i];
 #pragma unroll
             for (int r4 = 0; r4 < 4; ++r4) {
@@ -781,6 +780,13 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
               h[r4 * 4] = fmaf(x.x, w, h[r4 * 4]); h[r4 * 4 + 1] = fmaf(x.y, w, h[r4 * 4 + 1]);
               h[r4 * 4 + 2] = fmaf(x.z, w, h[r4 * 4 + 2]); h[r4 * 4 + 3] = fmaf(x.w, w, h[r4 * 4 + 3]);
             }
+          };
+          if constexpr (ND <= 4) {                 // D <= 4 (CartPole): the input features unrolled, their 16 shared-memory loads in
+#pragma unroll                                     // flight together (the rolled loop exposed one load latency per feature: 3.3 us per panel)
+            for (int i = 0; i < ND; ++i) if (i < D) feature(i);
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < D; ++i) feature(i);
           }
           const float bb = b1s[k];
           float* ps = R0 + rh * 16 * (H + 4) + k;
@@ -1579,12 +1585,12 @@ static size_t fused_smem(int B) { return sizeof(float) * (size_t)(SMALL_FLOATS +
 // Largest grid the cooperative launch can keep co-resident (one CTA per SM on B200) for minibatch size B.
 static const void* fused_fn(bool tc, int A, int D) {
   const int na = A <= 2 ? 0 : (A <= 4 ? 1 : 2), nd = D <= 4 ? 0 : 1;
-  // the FFMA instantiation keeps its round-1 generators (MAXD-strided tiles): one ND
-  static const void* const tab[3][3] = {
+  static const void* const tab[4][3] = {
+      {(const void*)ppo_epoch_kernel<false, 2, 4>, (const void*)ppo_epoch_kernel<false, 4, 4>, (const void*)ppo_epoch_kernel<false, 8, 4>},
       {(const void*)ppo_epoch_kernel<false, 2, 16>, (const void*)ppo_epoch_kernel<false, 4, 16>, (const void*)ppo_epoch_kernel<false, 8, 16>},
       {(const void*)ppo_epoch_kernel<true, 2, 4>, (const void*)ppo_epoch_kernel<true, 4, 4>, (const void*)ppo_epoch_kernel<true, 8, 4>},
       {(const void*)ppo_epoch_kernel<true, 2, 16>, (const void*)ppo_epoch_kernel<true, 4, 16>, (const void*)ppo_epoch_kernel<true, 8, 16>}};
-  return tab[tc ? 1 + nd : 0][na];
+  return tab[(tc ? 2 : 0) + nd][na];
 }
 
 static int fused_max_ctas(int B, bool tc = false, int A = 8, int D = 16) {
