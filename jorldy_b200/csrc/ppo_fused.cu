@@ -942,6 +942,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           }
         }
         __syncthreads();
+        TR(40);
         float g1 = 0.f, g2 = 0.f;
         for (int r = 0; r < a.world; ++r) {                  // rank order: identical bits on every rank
           const float* m = a.peer[a.rank] + a.xflag_off + JB_X_MSG + 4 * r;
@@ -1444,6 +1445,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           }
         }
         __syncthreads();
+        TR(41);
         {
           // this CTA owns chunk `cta` of slice `rank`
           const long long q4 = (a.P4 + a.world - 1) / a.world, c4 = (q4 + nctas - 1) / nctas;
@@ -1467,6 +1469,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
               if (r < a.world) st_sys4(a.peer[r] + a.xgred_off + 4 * i, sum);
           }
           const float tot = block_sum(sqa, scr + 64);                // (its barriers order every thread's stores before the tags)
+          TR(42);
           if (tid < a.world) {
             __threadfence_system();
             float* dst = a.peer[tid] + a.xflag_off + JB_X_PTAB + 2 * (a.rank * JB_X_MAX_CTAS + cta);
@@ -1474,6 +1477,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
             sys_flag_set(reinterpret_cast<unsigned int*>(dst) + 1, target);
           }
         }
+        TR(43);
         // every chunk of every owner has landed in this rank's copy of the averaged gradient?
         for (int e = tid; e < a.world * (int)nctas; e += NT) {
           const int r = e / (int)nctas, c = e - r * (int)nctas;
@@ -1484,6 +1488,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           }
         }
         __syncthreads();
+        TR(44);
         const float4* gr4 = reinterpret_cast<const float4*>(a.peer[a.rank] + a.xgred_off);
 #pragma unroll
         for (int it = 0; it < ADAM_IT; ++it) {

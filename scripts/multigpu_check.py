@@ -1,5 +1,6 @@
-"""2-GPU functional check (torchrun): PPO data-parallel learner (identical weights on every rank after
-learn), Ape-X sharded PER (global IS normalisation), NCCL all-reduce inside the captured graph."""
+"""Multi-GPU functional check (torchrun, >= 2 ranks): PPO data-parallel learner with the in-kernel gradient exchange
+(equal to the NCCL path to round-off, global critic means, identical weights on every rank after learn), Ape-X sharded
+PER (global IS normalisation)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
@@ -12,46 +13,66 @@ from jorldy_b200.core.collect import RolloutCollector, ReplayCollector
 # ---- PPO dp ----
 NE, NEP = int(os.environ.get("JB_NENV", 512)), int(os.environ.get("JB_NEPOCH", 2))
 env = Env("cartpole", num_envs=NE, seed=0, id=rank, device=dev)
-mk = lambda **kw: Agent("ppo", state_size=4, action_size=2, hidden_size=512, batch_size=256, n_step=32, n_epoch=NEP, device=dev,
-                        run_step=10**6, seed=100 + rank, **kw)
-agent = mk()
-agent.rng_stream_base = rank << 32
-parallel.attach(agent, world)
+
+
+def trio(**kw):
+    """The same learner three ways: persistent kernel with the in-kernel exchange, CUDA graphs + NCCL, eager + NCCL."""
+    mk = lambda **k2: Agent("ppo", state_size=4, action_size=2, hidden_size=512, batch_size=256, n_step=32, n_epoch=NEP, device=dev,
+                            run_step=10**6, seed=100 + rank, optim_config={"name": "adam", "lr": 2.5e-4}, **kw, **k2)
+    agent = mk()
+    agent.rng_stream_base = rank << 32
+    parallel.attach(agent, world)
+    ref_agent = mk(use_fused=False)
+    parallel.attach(ref_agent, world)
+    ref_agent.p2p = None
+    ref_agent.network.load_state_dict(agent.network.state_dict())
+    eag = mk(use_fused=False, use_cuda_graph=False)
+    parallel.attach(eag, world); eag.p2p = None
+    eag.network.load_state_dict(agent.network.state_dict())
+    return agent, ref_agent, eag
+
+
+def learn3(agents, ro):
+    out = []
+    for ag in agents:
+        ro.t = 32
+        torch.manual_seed(1234)
+        out.append(ag.learn_rollout(ro))
+        torch.cuda.synchronize()
+    return out
+
+
+n_steps_run = NEP * (NE * 32 // 256)
+# (1) exchange arithmetic: with the clip range wide open both critic candidates coincide (v_clip == v), so the fused kernel's
+# GLOBAL critic means and the NCCL path's per-rank ones select the same gradient and the three learners must agree to
+# fp32 round-off.  (Adam normalises every coordinate's step to ~lr, so coordinates whose gradient is pure round-off random-walk
+# apart between ANY two summation orders: the element-wise comparison is asserted for short runs only.)
+agent, ref_agent, eag = trio(epsilon_clip=1e9)
 print(f"rank {rank}: in-kernel gradient exchange {'ON' if agent.p2p else 'off (NCCL all-reduce)'}", flush=True)
-ref_agent = mk(use_fused=False)              # CUDA graphs + NCCL all-reduce: the reference for the fused exchange
-parallel.attach(ref_agent, world)
-ref_agent.p2p = None
-ref_agent.network.load_state_dict(agent.network.state_dict())
-eag = mk(use_fused=False, use_cuda_graph=False)      # eager multi-launch + NCCL: third opinion
-parallel.attach(eag, world); eag.p2p = None
-eag.network.load_state_dict(agent.network.state_dict())
 col = RolloutCollector(env, agent)
 ro = col.collect()
-torch.manual_seed(1234); res = agent.learn_rollout(ro)
-ro.t = 32
-torch.manual_seed(1234); res_ref = ref_agent.learn_rollout(ro)
-torch.cuda.synchronize()
-ro.t = 32
-torch.manual_seed(1234); res_eag = eag.learn_rollout(ro)
-torch.cuda.synchronize()
-print(f"rank {rank}: graph vs eager max|dW| = {(ref_agent.network.flat - eag.network.flat).abs().max().item():.3e}; "
-      f"fused vs eager = {(agent.network.flat - eag.network.flat).abs().max().item():.3e}", flush=True)
+res, res_ref, res_eag = learn3((agent, ref_agent, eag), ro)
 d = (agent.network.flat - ref_agent.network.flat).abs().max().item()
-for k in agent.network.p:
-    dk = (agent.network.p[k] - ref_agent.network.p[k]).abs().max().item()
-    print(f"rank {rank}:   {k:20s} max|fused-graph| = {dk:.3e}", flush=True)
-print(f"rank {rank}: fused(p2p={bool(agent.p2p)}) vs graph+NCCL after one learn(): max |dW| = {d:.3e}", {k: round(v, 4) for k, v in res.items()}, flush=True)
-n_steps_run = NEP * (NE * 32 // 256)
-# Adam normalises every coordinate's step to ~lr whatever the gradient's size, so coordinates whose gradient is pure
-# round-off (dead ReLU units) random-walk apart at lr per step between ANY two summation orders: the element-wise
-# comparison is only meaningful for a few steps; for long runs the learn() statistics and the bit-equality of the
-# weights across ranks (below) are the checks.
-# (the fused exchange uses the GLOBAL critic means, the NCCL path per-rank ones: identical while value == value_old,
-# i.e. on the first pass over fresh data, which is what the short run is)
+print(f"rank {rank}: [no clipping] graph vs eager max|dW| = {(ref_agent.network.flat - eag.network.flat).abs().max().item():.3e}; "
+      f"fused(p2p={bool(agent.p2p)}) vs graph+NCCL = {d:.3e} after {n_steps_run} steps", flush=True)
 if n_steps_run <= 8:
     assert d < 5e-5, d
 for k in res:
     assert abs(res[k] - res_ref[k]) < 5e-3 * max(1.0, abs(res_ref[k])), (k, res[k], res_ref[k])
+# (2) the reference's clip range: the fused kernel evaluates critic_loss = max(mean, mean) over the GLOBAL minibatch (identical
+# on every rank, equal to the reference's semantics); the NCCL path evaluates it per rank
+agent, ref_agent, eag = trio()
+col = RolloutCollector(env, agent)
+ro = col.collect()
+res, res_ref, _ = learn3((agent, ref_agent, eag), ro)
+cl = torch.tensor([res["critic_loss"], res_ref["critic_loss"]], dtype=torch.float64, device=dev)
+lo, hi = cl.clone(), cl.clone()
+dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+assert lo[0].item() == hi[0].item(), "the fused kernel's critic loss must be the same global number on every rank"
+print(f"rank {rank}: [clip 0.1] critic_loss fused (global) = {res['critic_loss']:.6f}; NCCL path (per rank) = {res_ref['critic_loss']:.6f} "
+      f"in [{lo[1].item():.6f}, {hi[1].item():.6f}]", {k: round(v, 4) for k, v in res.items()}, flush=True)
+for k in ("actor_loss", "entropy_loss", "mean_ret"):
+    assert abs(res[k] - res_ref[k]) < 2e-2 * max(1.0, abs(res_ref[k])), (k, res[k], res_ref[k])
 for it in range(3):
     res = agent.learn_rollout(col.collect())
 flat = agent.network.flat.clone()
