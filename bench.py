@@ -229,7 +229,7 @@ class PPOWorkload:
         ach = flops / (dur_ms * 1e-3) / 1e12
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ppo_epoch_kernel_traffic.json")))["dram_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_ppo_epoch_kernel_traffic.json")))["dram_bytes_per_launch"]
         except Exception:
             pass
         ffma = 148 * 128 * 2 * 1.965e-3
