@@ -124,15 +124,18 @@ struct Stager {
 // per launch instead of one per step; the host then raises (ppo.py checks acc[7]).  Time = SM cycles (clock64).
 constexpr long long X_TIMEOUT_CYCLES = 60ll * 1965000000ll;   // ~60 s of SM clock (clock64: a register read)
 constexpr int CTR_ABORT = 63;                           // a.barrier[CTR_ABORT] != 0: an exchange wait timed out
+// Polls are RELAXED sys-scope loads (an acquire load per poll costs a fence each time; measured: a release-signalled
+// one-way message took ~4 us end to end); one acq_rel fence after the flag is seen completes the acquire pattern.
 __device__ __forceinline__ bool sys_flag_wait(const unsigned int* flag, unsigned int target, unsigned int* abort_flag) {
   unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
-  if ((int)(v - target) >= 0) return true;
   const long long t0 = clock64();
   for (;;) {
-    for (int it = 0; it < 32; ++it) {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
-      if ((int)(v - target) >= 0) return true;
+    for (int it = 0; it < 64; ++it) {
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
+      if ((int)(v - target) >= 0) {
+        asm volatile("fence.acq_rel.sys;\n" ::: "memory");
+        return true;
+      }
     }
     unsigned int ab;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(ab) : "l"(abort_flag) : "memory");
@@ -929,25 +932,45 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         // row sums.  A peer's message for step s also says "I have finished step s-1", i.e. it no longer reads this
         // rank's gradient buffer, which the backward jobs below overwrite.
         const unsigned int target = a.xbase + (unsigned int)s + 1u;
+        // message = two 8-byte words {row sum | tag}: an aligned 64-bit store is single-copy atomic, so payload and tag need
+        // no fence between them (a release-signalled message cost ~4 us per step); that the peer no longer READS this rank's
+        // gradient follows from program order on the peer (its loads of step s-1 returned before it got here)
+        unsigned long long m1 = 0ull, m2 = 0ull;
         if (tid < a.world && tid != a.rank) {
           if (cta == 0) {
-            float* dst = a.peer[tid] + a.xflag_off + JB_X_MSG + 4 * a.rank;
-            st_sys1(dst, t1); st_sys1(dst + 1, t2);
-            sys_flag_set(reinterpret_cast<unsigned int*>(dst) + 2, target);      // release: orders the two values
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.peer[tid] + a.xflag_off + JB_X_MSG + 4 * a.rank);
+            const unsigned long long w1 = ((unsigned long long)target << 32) | (unsigned long long)__float_as_uint(t1);
+            const unsigned long long w2 = ((unsigned long long)target << 32) | (unsigned long long)__float_as_uint(t2);
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(dst), "l"(w1) : "memory");
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(dst + 1), "l"(w2) : "memory");
           }
-          const unsigned int* tag = reinterpret_cast<const unsigned int*>(a.peer[a.rank] + a.xflag_off + JB_X_MSG + 4 * tid) + 2;
-          if (!sys_flag_wait(tag, target, a.barrier + CTR_ABORT)) {
-            a.acc[7] = 1.f;
-            if (cta == 0) { a.partials[200] = 3.f; a.partials[201] = (float)tid; a.partials[202] = (float)s; a.partials[203] = (float)*tag; a.partials[204] = (float)target; }
+          const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.peer[a.rank] + a.xflag_off + JB_X_MSG + 4 * tid);
+          const long long t0 = clock64();
+          bool ok = false;
+          while (!ok) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(m1) : "l"(src) : "memory");
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(m2) : "l"(src + 1) : "memory");
+            ok = (int)((unsigned int)(m1 >> 32) - target) >= 0 && (int)((unsigned int)(m2 >> 32) - target) >= 0;
+            if (!ok) {
+              unsigned int ab;
+              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(ab) : "l"(a.barrier + CTR_ABORT) : "memory");
+              if (ab || clock64() - t0 > X_TIMEOUT_CYCLES) {
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(a.barrier + CTR_ABORT), "r"(1u) : "memory");
+                a.acc[7] = 1.f;
+                if (cta == 0) { a.partials[200] = 3.f; a.partials[201] = (float)tid; a.partials[202] = (float)s; a.partials[203] = (float)(unsigned int)(m1 >> 32); a.partials[204] = (float)target; }
+                break;
+              }
+            }
           }
+          scr[96 + 2 * tid] = __uint_as_float((unsigned int)m1);      // peers' row sums, read by every thread below
+          scr[96 + 2 * tid + 1] = __uint_as_float((unsigned int)m2);
         }
         __syncthreads();
         TR(40);
         float g1 = 0.f, g2 = 0.f;
         for (int r = 0; r < a.world; ++r) {                  // rank order: identical bits on every rank
-          const float* m = a.peer[a.rank] + a.xflag_off + JB_X_MSG + 4 * r;
-          g1 += r == a.rank ? t1 : ld_sys1(m);
-          g2 += r == a.rank ? t2 : ld_sys1(m + 1);
+          g1 += r == a.rank ? t1 : scr[96 + 2 * r];
+          g2 += r == a.rank ? t2 : scr[96 + 2 * r + 1];
         }
         t1 = g1; t2 = g2;
         invBW = invB / (float)a.world;
@@ -1434,10 +1457,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         const unsigned int target = a.xbase + (unsigned int)s + 1u;
         unsigned int* myx = reinterpret_cast<unsigned int*>(a.peer[a.rank] + a.xflag_off);
         if (tid < a.world && tid != a.rank) {
-          if (cta == 0) {                                            // this rank's gradient is complete (barrier above)
-            __threadfence_system();
+          if (cta == 0)     // this rank's gradient is complete (barrier above); the release store is the only system fence
             sys_flag_set(reinterpret_cast<unsigned int*>(a.peer[tid] + a.xflag_off) + JB_X_F1 + a.rank, target);
-          }
           const unsigned int* f1 = myx + JB_X_F1 + tid;
           if (!sys_flag_wait(f1, target, a.barrier + CTR_ABORT)) {
             a.acc[7] = 1.f;
@@ -1471,7 +1492,6 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           const float tot = block_sum(sqa, scr + 64);                // (its barriers order every thread's stores before the tags)
           TR(42);
           if (tid < a.world) {
-            __threadfence_system();
             float* dst = a.peer[tid] + a.xflag_off + JB_X_PTAB + 2 * (a.rank * JB_X_MAX_CTAS + cta);
             st_sys1(dst, tot);
             sys_flag_set(reinterpret_cast<unsigned int*>(dst) + 1, target);

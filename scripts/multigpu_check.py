@@ -57,8 +57,9 @@ print(f"rank {rank}: [no clipping] graph vs eager max|dW| = {(ref_agent.network.
       f"fused(p2p={bool(agent.p2p)}) vs graph+NCCL = {d:.3e} after {n_steps_run} steps", flush=True)
 if n_steps_run <= 8:
     assert d < 5e-5, d
-for k in res:
-    assert abs(res[k] - res_ref[k]) < 5e-3 * max(1.0, abs(res_ref[k])), (k, res[k], res_ref[k])
+for k in res:           # (critic_loss is REPORTED globally by the fused kernel, per rank by the NCCL path: compared in (2))
+    if k != "critic_loss":
+        assert abs(res[k] - res_ref[k]) < 5e-3 * max(1.0, abs(res_ref[k])), (k, res[k], res_ref[k])
 # (2) the reference's clip range: the fused kernel evaluates critic_loss = max(mean, mean) over the GLOBAL minibatch (identical
 # on every rank, equal to the reference's semantics); the NCCL path evaluates it per rank
 agent, ref_agent, eag = trio()
