@@ -124,19 +124,16 @@ struct Stager {
 // per launch instead of one per step; the host then raises (ppo.py checks acc[7]).  Time = SM cycles (clock64).
 constexpr long long X_TIMEOUT_CYCLES = 60ll * 1965000000ll;   // ~60 s of SM clock (clock64: a register read)
 constexpr int CTR_ABORT = 63;                           // a.barrier[CTR_ABORT] != 0: an exchange wait timed out
-// Polls are RELAXED sys-scope loads (an acquire load per poll costs a fence each time; measured: a release-signalled
-// one-way message took ~4 us end to end); one acq_rel fence after the flag is seen completes the acquire pattern.
+// Polls are ACQUIRE sys-scope loads.  (Measured alternatives at 2 GPUs: relaxed polls + one `fence.acq_rel.sys` after the
+// flag is seen made the step 10-20 us SLOWER, throttled or not — a full system fence per waiting thread costs far more than
+// the ordering an acquire load carries.)
 __device__ __forceinline__ bool sys_flag_wait(const unsigned int* flag, unsigned int target, unsigned int* abort_flag) {
   unsigned int v;
   const long long t0 = clock64();
   for (;;) {
-    for (int it = 0; it < 64; ++it) {
-      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
-      if ((int)(v - target) >= 0) {
-        asm volatile("fence.acq_rel.sys;\n" ::: "memory");
-        return true;
-      }
-      __nanosleep(100);       // un-throttled relaxed polls from 148 CTAs saturated L2 / the NVLink ingress: 93 us per step instead of 72
+    for (int it = 0; it < 32; ++it) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
+      if ((int)(v - target) >= 0) return true;
     }
     unsigned int ab;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(ab) : "l"(abort_flag) : "memory");
