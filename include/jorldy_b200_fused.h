@@ -43,8 +43,9 @@ typedef struct jb_ppo_fused_args {
    *                                 slice owner, then the owner stores its averaged slice into every rank)
    *   [xflag_off, +JB_X_WORDS)      32-bit words: JB_X_F1 "gradient of step s complete" per source rank,
    *                                 JB_X_MSG {sum (v-ret)^2, sum (v_clip-ret)^2, tag, -} per source rank (the two
-   *                                 critic means of ppo.py:151-154 are global), JB_X_PTAB {||slice chunk||^2, tag}
-   *                                 per (owner rank, owner CTA): a chunk's tag says "chunk stored in your copy".
+   *                                 critic means of ppo.py:151-154 are global), JB_X_PTAB ||slice chunk||^2 per (owner rank, owner CTA) and
+   *                                 JB_X_CNT, a counter per owner rank that its CTAs bump (red.release.sys) once their
+   *                                 chunk is stored in this rank's copy: 148 bumps per step.
    * Tags are monotonic: xbase = number of steps run by earlier launches. */
   float *peer[8];
   int world, rank;
@@ -57,6 +58,7 @@ typedef struct jb_ppo_fused_args {
 
 /* word offsets inside the flag region of the exchange buffer */
 #define JB_X_F1 0
+#define JB_X_CNT 16                    /* per owner rank: number of chunk publications so far (remote red.add) */
 #define JB_X_MSG 64
 #define JB_X_PTAB 128
 #define JB_X_MAX_CTAS 256
