@@ -37,20 +37,19 @@ typedef struct jb_ppo_fused_args {
   long long *cursor;                 /* minibatch cursor (device) */
   const float *lr;                   /* learning rate (device scalar) */
   /* multi-GPU: gradient exchange through peer-mapped memory (world == 1: unused).  peer[r] = rank r's exchange
-   * buffer, laid out in floats as
-   *   [0, 4*P4)                     this rank's gradient (`grad` above is peer[rank])
-   *   [xgred_off, xgred_off+4*P4)   the AVERAGED gradient: slice q of it is written by rank q (reduce-scatter by the
-   *                                 slice owner, then the owner stores its averaged slice into every rank)
-   *   [xflag_off, +JB_X_WORDS)      32-bit words: JB_X_F1 "gradient of step s complete" per source rank,
-   *                                 JB_X_MSG {sum (v-ret)^2, sum (v_clip-ret)^2, tag, -} per source rank (the two
-   *                                 critic means of ppo.py:151-154 are global), JB_X_PTAB ||slice chunk||^2 per (owner rank, owner CTA) and
-   *                                 JB_X_CNT, a counter per owner rank that its CTAs bump (red.release.sys) once their
-   *                                 chunk is stored in this rank's copy: 148 bumps per step.
-   * Tags are monotonic: xbase = number of steps run by earlier launches. */
+   * buffer, laid out in 32-bit words as
+   *   [0, 4*P4)                       this rank's gradient (`grad` above is peer[rank])
+   *   [xllin_off, + 8*world*q4)       inbox of the slice this rank OWNS (q4 = ceil(P4 / world) float4): for every source
+   *                                   rank the raw gradient slice as "LL" words {tag | value} (64 bit each)
+   *   [xgred_off, + 8*P4)             the AVERAGED gradient as LL words: slice q is written by its owner, rank q
+   *   [xflag_off, + JB_X_WORDS)       JB_X_MSG {critic row sum | tag} x 2 per source rank (the two critic means of
+   *                                   ppo.py:151-154 are global), JB_X_PTAB {||chunk||^2 | tag} per (owner rank, owner CTA)
+   * An LL word is valid when its tag equals the step number: no flags, no fences.  Tags are monotonic: xbase = number
+   * of steps run by earlier launches. */
   float *peer[8];
   int world, rank;
   unsigned int xbase;
-  int xflag_off, xgred_off;
+  int xflag_off, xgred_off, xllin_off;
   int nh[3];                         /* outputs per head */
   int B, D, H, A, nout, continuous, n_steps;
   float eps_clip, vf_coef, ent_coef, beta1, beta2, adam_eps, max_norm;

@@ -17,7 +17,7 @@ class FusedArgs(ctypes.Structure):
         ("state", _P), ("action", _P), ("adv", _P), ("ret", _P), ("vold", _P), ("logp_old", _P), ("perm", _P),
         ("h1", _P), ("h2", _P), ("xg", _P), ("w1p", _P), ("headp", _P), ("h2t", _P), ("W2t", _P), ("W2img", _P), ("W2Timg", _P), ("partials", _P), ("acc", _P),
         ("cur_idx", _P), ("barrier", _P), ("step", _P), ("cursor", _P), ("lr", _P),
-        ("peer", _P * 8), ("world", ctypes.c_int), ("rank", ctypes.c_int), ("xbase", ctypes.c_uint), ("xflag_off", ctypes.c_int), ("xgred_off", ctypes.c_int),
+        ("peer", _P * 8), ("world", ctypes.c_int), ("rank", ctypes.c_int), ("xbase", ctypes.c_uint), ("xflag_off", ctypes.c_int), ("xgred_off", ctypes.c_int), ("xllin_off", ctypes.c_int),
         ("nh", ctypes.c_int * 3),
         ("B", ctypes.c_int), ("D", ctypes.c_int), ("H", ctypes.c_int), ("A", ctypes.c_int), ("nout", ctypes.c_int),
         ("continuous", ctypes.c_int), ("n_steps", ctypes.c_int),
@@ -100,8 +100,8 @@ class FusedRunner:
             for r in range(8):
                 a.peer[r] = p2p["ptrs"][r] if r < p2p["world"] else None
             a.world, a.rank, a.xbase, a.xflag_off = p2p["world"], p2p["rank"], p2p["epoch"] & 0xFFFFFFFF, p2p["flag_off"]
-            a.xgred_off = p2p["gred_off"]
+            a.xgred_off, a.xllin_off = p2p["gred_off"], p2p["llin_off"]
             p2p["epoch"] += int(n_steps)
         else:
-            a.world, a.rank, a.xbase, a.xflag_off, a.xgred_off = 1, 0, 0, 0, 0
+            a.world, a.rank, a.xbase, a.xflag_off, a.xgred_off, a.xllin_off = 1, 0, 0, 0, 0, 0
         C.jb_ppo_fused_run(ctypes.addressof(a), stream_ptr())

@@ -36,7 +36,9 @@ def _try_p2p(agent, world_size):
         import torch.distributed._symmetric_memory as symm
         if net.num_flat % 4:
             raise RuntimeError("flat parameter buffer is not a whole number of float4")
-        n = 2 * net.num_flat + P2P_FLAG_WORDS     # gradient | averaged gradient | flag words
+        q4 = (net.num_flat // 4 + world_size - 1) // world_size
+        llin, llout = 8 * world_size * q4, 2 * net.num_flat          # 64-bit LL words, counted in floats
+        n = net.num_flat + llin + llout + P2P_FLAG_WORDS             # gradient | owner inbox | averaged gradient | message words
         buf = symm.empty(n, dtype=torch.float32, device=net.flat.device)
         buf.zero_()
         torch.cuda.synchronize()
@@ -68,7 +70,7 @@ def _try_p2p(agent, world_size):
     net.rebind_grad(buf)
     dist.barrier()
     agent.p2p = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "rank": dist.get_rank(), "world": world_size, "epoch": 0,
-                 "gred_off": net.num_flat, "flag_off": 2 * net.num_flat}
+                 "llin_off": net.num_flat, "gred_off": net.num_flat + llin, "flag_off": net.num_flat + llin + llout}
 
 
 def attach(agent, world_size, average_with="avg"):

@@ -34,18 +34,22 @@
 // (L2), and the barrier's gpu-scope release/acquire orders the phases.
 //
 // Multi-GPU (args.world > 1): every rank's flat gradient lives in a peer-mapped exchange buffer (args.peer[r],
-// torch symmetric memory) and the gradient average is a reduce-scatter + all-gather done by the kernel itself:
-//   * after the backward phase's barrier CTA 0 tells every peer "gradient of step s complete" (one flag word each);
-//   * rank q OWNS slice q of the flat gradient, CTA c of rank q chunk c of that slice: it reads the chunk from all
-//     ranks (NVLink loads, all in flight), sums in rank order, scales by 1/world, stores the averaged chunk into
-//     EVERY rank's "averaged gradient" buffer (NVLink stores) and then publishes {||chunk||^2, tag} to every rank;
-//   * every CTA waits for the tags of all world x grid chunks, folds the partial norms in a fixed order (identical
-//     bits on all ranks) and applies clip + Adam to its slice of the local copy of the averaged gradient.
-//   Per step and rank this moves 2 (world-1)/world of the gradient over NVLink (the first version read every
-//   rank's full gradient: world-1 times) and needs no grid barrier beyond the single-GPU three.
-//   * the two scalar means of critic_loss = max(mean, mean) (ppo.py:151-154) are GLOBAL: each rank sends its two row
-//     sums to the peers during the row phase (16-byte message + tag); receiving step s's message from a peer also
-//     proves that the peer has finished reading this rank's gradient of step s-1, so it may be overwritten.
+// torch symmetric memory) and the gradient average is a reduce-scatter + all-gather done by the kernel itself in
+// "LL" words: every 32-bit datum crosses NVLink as one aligned 64-bit word {step tag | value}, which is valid exactly
+// when its tag equals the step number (64-bit stores are single-copy atomic) — no flags, no fences, one NVLink traversal
+// per hop.  After the backward phase's barrier
+//   * every CTA pushes its chunk of every other rank's slice of the local gradient into that owner's inbox;
+//   * rank q OWNS slice q, CTA c of rank q chunk c of it: it sums the ranks' copies in rank order, scales by 1/world,
+//     pushes the averaged chunk into EVERY rank's copy of the averaged gradient and the chunk's squared norm into every
+//     rank's norm table;
+//   * every CTA reads its Adam slice of the averaged gradient and all chunk norms as they arrive, folds the norms in a
+//     fixed order (identical bits on all ranks) and applies clip + Adam.
+//   Measured history at 2 GPUs (profiles/r02_exchange.md): flag + fence protocols cost 3.5-6 us PER HOP (release store or
+//   system fence waiting for remote write acknowledgements; acquire polls), 64-72 us per step; un-throttled relaxed polling
+//   of flags saturated L2 (93 us).
+//   * the two scalar means of critic_loss = max(mean, mean) (ppo.py:151-154) are GLOBAL: each rank sends its two row sums to
+//     the peers during the row phase (two LL words); receiving step s's message from a peer also proves that the peer has
+//     finished step s-1.
 // No NCCL call between backward and Adam.
 //
 // Constraints (else the host uses the multi-launch path): B % 32 == 0, B <= 512, H % 32 == 0, H <= 512,
@@ -157,6 +161,56 @@ __device__ __forceinline__ float ld_sys1(const float* p) {
 }
 __device__ __forceinline__ void st_sys1(float* p, float v) {
   asm volatile("st.relaxed.sys.global.f32 [%0], %1;\n" ::"l"(p), "f"(v) : "memory");
+}
+// ---- "LL" words (NCCL's low-latency idea): every 32-bit datum travels as one aligned 64-bit word {tag | value}; an aligned 64-bit
+// store is single-copy atomic, so a word whose tag equals the step number carries a valid value — no flag, no fence, no
+// ordering between different words is needed, and the latency of an exchange hop is one NVLink traversal.
+__device__ __forceinline__ unsigned long long ll_pack(float v, unsigned int tag) {
+  return ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+}
+__device__ __forceinline__ void ll_store4(unsigned long long* dst /* 4 words, 32-byte aligned */, float4 v, unsigned int tag) {
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};\n" ::"l"(dst), "l"(ll_pack(v.x, tag)), "l"(ll_pack(v.y, tag)) : "memory");
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};\n" ::"l"(dst + 2), "l"(ll_pack(v.z, tag)), "l"(ll_pack(v.w, tag)) : "memory");
+}
+// spins until the four words at src carry `tag`; false after the exchange time-out (or once another wait has given up)
+__device__ __forceinline__ bool ll_load4(const unsigned long long* src, unsigned int tag, float4& v, unsigned int* abort_flag) {
+  unsigned long long w0, w1, w2, w3;
+  const long long t0 = clock64();
+  for (int it = 0;; ++it) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(w2), "=l"(w3) : "l"(src + 2) : "memory");
+    if ((unsigned int)(w0 >> 32) == tag && (unsigned int)(w1 >> 32) == tag && (unsigned int)(w2 >> 32) == tag && (unsigned int)(w3 >> 32) == tag) break;
+    if ((it & 63) == 63) {
+      unsigned int ab;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(ab) : "l"(abort_flag) : "memory");
+      if (ab || clock64() - t0 > X_TIMEOUT_CYCLES) {
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(abort_flag), "r"(1u) : "memory");
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        return false;
+      }
+    }
+  }
+  v = make_float4(__uint_as_float((unsigned int)w0), __uint_as_float((unsigned int)w1), __uint_as_float((unsigned int)w2), __uint_as_float((unsigned int)w3));
+  return true;
+}
+__device__ __forceinline__ bool ll_load1(const unsigned long long* src, unsigned int tag, float& v, unsigned int* abort_flag) {
+  unsigned long long w;
+  const long long t0 = clock64();
+  for (int it = 0;; ++it) {
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(w) : "l"(src) : "memory");
+    if ((unsigned int)(w >> 32) == tag) break;
+    if ((it & 63) == 63) {
+      unsigned int ab;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(ab) : "l"(abort_flag) : "memory");
+      if (ab || clock64() - t0 > X_TIMEOUT_CYCLES) {
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(abort_flag), "r"(1u) : "memory");
+        v = 0.f;
+        return false;
+      }
+    }
+  }
+  v = __uint_as_float((unsigned int)w);
+  return true;
 }
 __device__ __forceinline__ float4 ld_sys4(const float* p) {
   float4 v;
@@ -1452,70 +1506,71 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
           if (i < hi) gg[it] = __ldcg(g4 + i);
         }
       } else {
-        // ---- gradient average over peer memory (NVLink): reduce-scatter by the slice owners + all-gather by stores
+        // ---- gradient average over peer memory (NVLink): reduce-scatter to the slice owners + all-gather, both as LL words
         const unsigned int target = a.xbase + (unsigned int)s + 1u;
-        unsigned int* myx = reinterpret_cast<unsigned int*>(a.peer[a.rank] + a.xflag_off);
-        if (tid < a.world && tid != a.rank) {
-          if (cta == 0)     // this rank's gradient is complete (barrier above); the release store is the only system fence
-            sys_flag_set(reinterpret_cast<unsigned int*>(a.peer[tid] + a.xflag_off) + JB_X_F1 + a.rank, target);
-          const unsigned int* f1 = myx + JB_X_F1 + tid;
-          if (!sys_flag_wait(f1, target, a.barrier + CTR_ABORT)) {
-            a.acc[7] = 1.f;
-            if (cta == 0) { a.partials[200] = 1.f; a.partials[201] = (float)tid; a.partials[202] = (float)s; a.partials[203] = (float)*f1; a.partials[204] = (float)target; }
-          }
+        unsigned int* abortf = a.barrier + CTR_ABORT;
+        const long long q4 = (a.P4 + a.world - 1) / a.world, c4 = (q4 + nctas - 1) / nctas;
+        bool ok = true;
+        // (1) push: this CTA's chunk of every OTHER owner's slice of the local gradient -> that owner's inbox [src = me]
+        for (int q = 0; q < a.world; ++q) {
+          if (q == a.rank) continue;
+          const long long sl_lo = (long long)q * q4, sl_hi = min(a.P4, sl_lo + q4);
+          const long long ch_lo = sl_lo + (long long)cta * c4, ch_hi = min(sl_hi, ch_lo + c4);
+          unsigned long long* inbox = reinterpret_cast<unsigned long long*>(a.peer[q] + a.xllin_off) + ((size_t)a.rank * q4) * 4;
+          for (long long i = ch_lo + tid; i < ch_hi; i += NT) ll_store4(inbox + (i - sl_lo) * 4, __ldcg(g4 + i), target);
         }
-        __syncthreads();
         TR(41);
         {
-          // this CTA owns chunk `cta` of slice `rank`
-          const long long q4 = (a.P4 + a.world - 1) / a.world, c4 = (q4 + nctas - 1) / nctas;
-          const long long sl_hi = min(a.P4, (long long)(a.rank + 1) * q4);
-          const long long ch_lo = (long long)a.rank * q4 + (long long)cta * c4, ch_hi = min(sl_hi, ch_lo + c4);
+          // (2) this CTA owns chunk `cta` of slice `rank`: sum the ranks' copies in rank order (the same bits whoever owns the
+          // chunk), scale, and send the averaged chunk to every rank's copy of the averaged gradient
+          const long long sl_lo = (long long)a.rank * q4, sl_hi = min(a.P4, sl_lo + q4);
+          const long long ch_lo = sl_lo + (long long)cta * c4, ch_hi = min(sl_hi, ch_lo + c4);
+          const unsigned long long* inbox = reinterpret_cast<const unsigned long long*>(a.peer[a.rank] + a.xllin_off);
           const float inv_world = 1.f / (float)a.world;
           float sqa = 0.f;
           for (long long i = ch_lo + tid; i < ch_hi; i += NT) {
-            float4 t[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r)                              // all ranks' loads in flight together
-              if (r < a.world) t[r] = r == a.rank ? __ldcg(g4 + i) : ld_sys4(a.peer[r] + 4 * i);
             float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int r = 0; r < 8; ++r)                              // rank order: the same bits whoever owns the chunk
-              if (r < a.world) { sum.x += t[r].x; sum.y += t[r].y; sum.z += t[r].z; sum.w += t[r].w; }
+            for (int r = 0; r < a.world; ++r) {
+              float4 t;
+              if (r == a.rank) t = __ldcg(g4 + i);
+              else ok = ll_load4(inbox + ((size_t)r * q4 + (i - sl_lo)) * 4, target, t, abortf) && ok;
+              sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+            }
             sum.x *= inv_world; sum.y *= inv_world; sum.z *= inv_world; sum.w *= inv_world;
             sqa = fmaf(sum.x, sum.x, sqa); sqa = fmaf(sum.y, sum.y, sqa); sqa = fmaf(sum.z, sum.z, sqa); sqa = fmaf(sum.w, sum.w, sqa);
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-              if (r < a.world) st_sys4(a.peer[r] + a.xgred_off + 4 * i, sum);
+            for (int r = 0; r < a.world; ++r)
+              ll_store4(reinterpret_cast<unsigned long long*>(a.peer[r] + a.xgred_off) + (size_t)i * 4, sum, target);
           }
-          const float tot = block_sum(sqa, scr + 64);                // (its barriers order every thread's stores before the tags)
+          const float tot = block_sum(sqa, scr + 64);
           TR(42);
-          if (tid < a.world) {
-            // publish: the chunk's norm, then ONE release bump of this owner's counter in rank `tid`'s buffer (the release orders
-            // every thread's chunk stores, seen through the barriers above, before the bump).  Waiters poll `world` counters
-            // instead of world x 148 tags: ~150x fewer sys-scope acquire loads per step.
-            float* base = a.peer[tid] + a.xflag_off;
-            st_sys1(base + JB_X_PTAB + 2 * (a.rank * JB_X_MAX_CTAS + cta), tot);
-            asm volatile("red.release.sys.global.add.u32 [%0], 1;\n" ::"l"(reinterpret_cast<unsigned int*>(base) + JB_X_CNT + a.rank) : "memory");
+          if (tid < a.world) {                                        // the chunk's squared norm, one LL word per destination rank
+            unsigned long long* pt = reinterpret_cast<unsigned long long*>(a.peer[tid] + a.xflag_off + JB_X_PTAB) + (a.rank * JB_X_MAX_CTAS + cta);
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(pt), "l"(ll_pack(tot, target)) : "memory");
           }
         }
         TR(43);
-        // every chunk of every owner has landed in this rank's copy of the averaged gradient?
-        if (tid < a.world) {
-          const unsigned int* cnt = myx + JB_X_CNT + tid;
-          if (!sys_flag_wait(cnt, target * nctas, a.barrier + CTR_ABORT)) {
-            a.acc[7] = 1.f;
-            if (cta == 0) { a.partials[200] = 2.f; a.partials[201] = (float)tid; a.partials[202] = (float)s; a.partials[203] = (float)*cnt; a.partials[204] = (float)(target * nctas); }
-          }
-        }
-        __syncthreads();
-        TR(44);
-        const float4* gr4 = reinterpret_cast<const float4*>(a.peer[a.rank] + a.xgred_off);
+        // (3) this CTA's Adam slice of the averaged gradient (words arrive from all owners), and all chunk norms
+        const unsigned long long* avg = reinterpret_cast<const unsigned long long*>(a.peer[a.rank] + a.xgred_off);
 #pragma unroll
         for (int it = 0; it < ADAM_IT; ++it) {
           const long long i = lo + tid + it * NT;
-          if (i < hi) gg[it] = __ldcg(gr4 + i);
+          if (i < hi) ok = ll_load4(avg + (size_t)i * 4, target, gg[it], abortf) && ok;
         }
+        if (tid < (int)nctas) {
+          const unsigned long long* pt = reinterpret_cast<const unsigned long long*>(a.peer[a.rank] + a.xflag_off + JB_X_PTAB);
+          float t = 0.f;
+          for (int r = 0; r < a.world; ++r) {                         // owner-rank order
+            float v;
+            ok = ll_load1(pt + (r * JB_X_MAX_CTAS + tid), target, v, abortf) && ok;
+            t += v;
+          }
+          dvs[tid] = t;
+        }
+        if (!ok) {
+          a.acc[7] = 1.f;
+          if (cta == 0) { a.partials[200] = 1.f; a.partials[201] = (float)tid; a.partials[202] = (float)s; a.partials[204] = (float)target; }
+        }
+        TR(44);
       }
       // next step's state rows (sidx was published before the barrier)
       float xv[2] = {0.f, 0.f};
@@ -1530,15 +1585,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
         for (int q = 0; q < 2; ++q) { const int e = tid + q * NT, r = e >> 4, i = e & 15; if (i < D) xv[q] = a.state[(size_t)sidx[r] * D + i]; }
       }
       // ||g||: one coalesced read of the partials per CTA, then every warp folds them in the same fixed order
-      if (tid < (int)nctas) {
-        if (a.world == 1) dvs[tid] = ldcg(a.partials + tid);
-        else {                                       // chunk norms of all owners, owner-rank order
-          const float* pt = a.peer[a.rank] + a.xflag_off + JB_X_PTAB;
-          float t = 0.f;
-          for (int r = 0; r < a.world; ++r) t += ld_sys1(pt + 2 * (r * JB_X_MAX_CTAS + tid));
-          dvs[tid] = t;
-        }
-      }
+      if (a.world == 1 && tid < (int)nctas) dvs[tid] = ldcg(a.partials + tid);     // (multi-GPU: filled by the exchange above)
       if (s + 1 < a.n_steps) gather_rows();        // next step's rollout values (row ids were loaded in P3)
       __syncthreads();
       float pv[NT / 32];
@@ -1580,7 +1627,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_epoch_kernel(Args a, int dsm_floats
       }
       for (long long i = lo + tid + (long long)ADAM_IT * NT; i < hi; i += NT) {   // slices beyond 8 K floats per CTA
         float4 p_ = __ldcg(p4 + i), m_ = __ldcg(m4 + i), v_ = __ldcg(v4 + i);
-        const float4 g_ = __ldcg((a.world > 1 ? reinterpret_cast<const float4*>(a.peer[a.rank] + a.xgred_off) : g4) + i);
+        float4 g_;
+        if (a.world > 1) {
+          if (!ll_load4(reinterpret_cast<const unsigned long long*>(a.peer[a.rank] + a.xgred_off) + (size_t)i * 4, a.xbase + (unsigned int)s + 1u, g_, a.barrier + CTR_ABORT)) a.acc[7] = 1.f;
+        } else g_ = __ldcg(g4 + i);
         upd(p_.x, g_.x, m_.x, v_.x); upd(p_.y, g_.y, m_.y, v_.y); upd(p_.z, g_.z, m_.z, v_.z); upd(p_.w, g_.w, m_.w, v_.w);
         p4[i] = p_; m4[i] = m_; v4[i] = v_;
         shadow(i, p_);
@@ -1662,8 +1712,9 @@ JB_API int jb_ppo_fused_run(const void* host_args, void* stream) {
   if (ctas > NT) ctas = NT;
   if (a.world < 1 || a.world > 8 || a.rank < 0 || a.rank >= a.world) return JB_ERR_INVALID;
   if (a.world > 1) {   // grad must be this rank's exchange buffer: gradient | averaged gradient | flag words
-    if (a.peer[a.rank] != a.grad || a.xgred_off < a.P4 * 4 || a.xflag_off < a.xgred_off + a.P4 * 4 || (a.xgred_off & 3) ||
-        (a.xflag_off & 3) || ctas > JB_X_MAX_CTAS)
+    const long long q4 = (a.P4 + a.world - 1) / a.world;
+    if (a.peer[a.rank] != a.grad || a.xllin_off < a.P4 * 4 || a.xgred_off < a.xllin_off + 8 * a.world * q4 ||
+        a.xflag_off < a.xgred_off + 8 * a.P4 || (a.xllin_off & 7) || (a.xgred_off & 7) || (a.xflag_off & 3) || ctas > JB_X_MAX_CTAS)
       return JB_ERR_INVALID;
     for (int r = 0; r < a.world; ++r) if (!a.peer[r]) return JB_ERR_INVALID;
   }
