@@ -56,8 +56,6 @@ typedef struct jb_ppo_fused_args {
 } jb_ppo_fused_args;
 
 /* word offsets inside the flag region of the exchange buffer */
-#define JB_X_F1 0
-#define JB_X_CNT 16                    /* per owner rank: number of chunk publications so far (remote red.add) */
 #define JB_X_MSG 64
 #define JB_X_PTAB 128
 #define JB_X_MAX_CTAS 256

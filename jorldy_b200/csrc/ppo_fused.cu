@@ -122,46 +122,13 @@ struct Stager {
   }
 };
 
-// ---- cross-GPU flag wait (multi-GPU gradient exchange): bounded by WALL-CLOCK time (a peer may legitimately be
-// seconds late: it is another process with its own host-side launch sequence), and once one wait has given up every
-// later wait returns at once (`abort_flag`, a word of this GPU's barrier block), so that a dead peer costs one timeout
-// per launch instead of one per step; the host then raises (ppo.py checks acc[7]).  Time = SM cycles (clock64).
+// ---- cross-GPU waits (multi-GPU gradient exchange) are bounded in time (a peer may legitimately be seconds late: it is
+// another process with its own host-side launch sequence), and once one wait has given up every later wait returns at once
+// (`abort_flag`, a word of this GPU's barrier block), so that a dead peer costs one time-out per launch instead of one per
+// step; the host then raises (ppo.py checks acc[7]).  Time = SM cycles (clock64: a register read; %globaltimer costs
+// microseconds per read).
 constexpr long long X_TIMEOUT_CYCLES = 60ll * 1965000000ll;   // ~60 s of SM clock (clock64: a register read)
 constexpr int CTR_ABORT = 63;                           // a.barrier[CTR_ABORT] != 0: an exchange wait timed out
-// Polls are ACQUIRE sys-scope loads.  (Measured alternatives at 2 GPUs: relaxed polls + one `fence.acq_rel.sys` after the
-// flag is seen made the step 10-20 us SLOWER, throttled or not — a full system fence per waiting thread costs far more than
-// the ordering an acquire load carries.)
-__device__ __forceinline__ bool sys_flag_wait(const unsigned int* flag, unsigned int target, unsigned int* abort_flag) {
-  unsigned int v;
-  const long long t0 = clock64();
-  for (;;) {
-    for (int it = 0; it < 32; ++it) {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
-      if ((int)(v - target) >= 0) return true;
-    }
-    unsigned int ab;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(ab) : "l"(abort_flag) : "memory");
-    if (ab) return false;
-    if (clock64() - t0 > X_TIMEOUT_CYCLES) {
-      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(abort_flag), "r"(1u) : "memory");
-      return false;
-    }
-  }
-}
-__device__ __forceinline__ void sys_flag_set(unsigned int* flag, unsigned int value) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(flag), "r"(value) : "memory");
-}
-__device__ __forceinline__ void st_sys4(float* p, float4 v) {
-  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float ld_sys1(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_sys1(float* p, float v) {
-  asm volatile("st.relaxed.sys.global.f32 [%0], %1;\n" ::"l"(p), "f"(v) : "memory");
-}
 // ---- "LL" words (NCCL's low-latency idea): every 32-bit datum travels as one aligned 64-bit word {tag | value}; an aligned 64-bit
 // store is single-copy atomic, so a word whose tag equals the step number carries a valid value — no flag, no fence, no
 // ordering between different words is needed, and the latency of an exchange hop is one NVLink traversal.
@@ -211,11 +178,6 @@ __device__ __forceinline__ bool ll_load1(const unsigned long long* src, unsigned
   }
   v = __uint_as_float((unsigned int)w);
   return true;
-}
-__device__ __forceinline__ float4 ld_sys4(const float* p) {
-  float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
 }
 
 // ---- grid barrier (all CTAs co-resident: cooperative launch) ------------------------------------------
