@@ -210,4 +210,43 @@ JB_API int jb_rmsprop_centered_step(float* p, const float* g, float* square_avg,
                                     float max_norm, float* norm_out, void* stream);
 JB_API int jb_copy_f32(float* dst, const float* src, long long P, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Continuous off-policy family — jorldy/core/agent/ddpg.py, td3.py, sac.py; the row / element-wise
+ * steps between the dense layers (csrc/actor_critic.cu).
+ *   jb_soft_update     t := tau p + (1 - tau) t over a flat buffer            ddpg.py:160-164, td3.py:190-196, sac.py:262-266
+ *   jb_tanh_act        out = clip(tanh(pre) + clip(noise*scale, +-noise_clip), +-out_clip); noise NULL: plain tanh head
+ *                      (network/policy.py:19-20; td3.py:141-142 act noise; td3.py:153-156 target smoothing)
+ *   jb_tanh_bwd        dpre = da (1 - a^2)
+ *   jb_ou_act          action = tanh(pre) + clip(X, +-1) with one Ornstein-Uhlenbeck process X[M,A] (f64) per env row and
+ *                      ONE normal per row and step (agent/utils.py:8-26, ddpg.py:113-118); greedy: tanh(pre)
+ *   jb_philox_fill     standard normals (kind 0) / uniforms in [lo,hi) (kind 1) from the device Philox stream
+ *   jb_ac_critic_loss  y = r + ((1-d) gamma)(min(nq1,nq2) + alpha(-next_logp)); dq_i = 2(q_i - y)/B;
+ *                      stats = {mse1, mse2, max y}; q2/nq2/alpha/next_logp may be NULL    ddpg.py:131-136, td3.py:150-168, sac.py:172-204
+ *   jb_ac_neg_mean     stat = -mean(q), dq = -1/B                              ddpg.py:143-144, td3.py:176-177
+ *   jb_sac_sample      a = tanh(mu + std eps), logp with the tanh correction  sac.py:151-160, network/policy.py:50-56
+ *   jb_sac_minq        dq_i of L = mean(alpha logp - min(q1,q2)); stats = {L, mean min q, mean entropy, mean entropy - target}
+ *   jb_sac_actor_bwd   d L / d (raw mu | raw log_std) [B,2A] from d L / d action and the alpha logp term   sac.py:222-236
+ *   jb_sac_alpha       alpha_loss = log_alpha * stats4[3]; alpha := exp(log_alpha); grad := stats4[3]     sac.py:238-246
+ * ------------------------------------------------------------------------------------------- */
+JB_API int jb_soft_update(float* target, const float* online, int64_t n, double tau, void* stream);
+JB_API int jb_tanh_act(const float* pre, const float* noise, int64_t n, float scale, float noise_clip, float out_clip,
+                       float* out, void* stream);
+JB_API int jb_tanh_bwd(const float* da, const float* a, int64_t n, float* dpre, void* stream);
+JB_API int jb_ou_act(const float* pre, int M, int A, double* X, const double* normal, uint64_t seed, uint64_t stream_base,
+                     long long* row_ctr, double theta, double mu, double sigma, int greedy, float* action, void* stream);
+JB_API int jb_philox_fill(float* out, int64_t n, int kind, float lo, float hi, uint64_t seed, uint64_t stream_base,
+                          uint64_t ctr, long long* ctr_dev, void* stream);
+JB_API int jb_ac_critic_loss(const float* q1, const float* q2, const float* nq1, const float* nq2, const float* alpha,
+                             const float* next_logp, const float* reward, const float* done, int B, float gamma,
+                             float* dq1, float* dq2, float* stats, void* stream);
+JB_API int jb_ac_neg_mean(const float* q, int B, float* dq, float* stat, void* stream);
+JB_API int jb_sac_sample(const float* raw, int nout, const float* eps, int M, int A, float* action, float* logp,
+                         void* stream);
+JB_API int jb_sac_minq(const float* q1, const float* q2, const float* logp, const float* alpha, float target_entropy,
+                       int B, float* dq1, float* dq2, float* stats, void* stream);
+JB_API int jb_sac_actor_bwd(const float* raw, int nout, const float* eps, const float* action, const float* da,
+                            const float* alpha, int B, int A, float* dout, void* stream);
+JB_API int jb_sac_alpha(const float* log_alpha, const float* stats4, float* alpha, float* grad, float* alpha_loss,
+                        void* stream);
+
 #endif /* JORLDY_B200_H */

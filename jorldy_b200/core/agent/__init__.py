@@ -3,9 +3,11 @@ from collections import OrderedDict
 
 from .ppo import PPO
 from .dqn import DQN, Double, Dueling, Multistep, PER, Noisy, C51, Rainbow, ApeX
+from .ddpg import DDPG, TD3, SAC
 
-agent_dict = OrderedDict(sorted(dict(ape_x=ApeX, c51=C51, double=Double, dqn=DQN, dueling=Dueling, multistep=Multistep,
-                                     noisy=Noisy, per=PER, ppo=PPO, rainbow=Rainbow).items()))
+agent_dict = OrderedDict(sorted(dict(ape_x=ApeX, c51=C51, ddpg=DDPG, double=Double, dqn=DQN, dueling=Dueling,
+                                     multistep=Multistep, noisy=Noisy, per=PER, ppo=PPO, rainbow=Rainbow, sac=SAC,
+                                     td3=TD3).items()))
 
 
 def register(name, cls):

@@ -124,7 +124,7 @@ class ReplayCollector:
             state = env.obs.clone()
             action, q_sel = agent.act_device(agent._net_input(state), True)
             next_obs, reward, done = env.step_device(action)
-            tr = {"state": state, "action": action.view(-1, 1).clone(), "reward": reward.clone(), "done": done.clone(),
+            tr = {"state": state, "action": action.view(action.shape[0], -1).clone(), "reward": reward.clone(), "done": done.clone(),
                   "next_state": next_obs.clone()}
             if self.assembler is not None:
                 if self.assembler.apex:

@@ -15,6 +15,20 @@ import torch.distributed as dist
 P2P_FLAG_WORDS = 128 + 8 * 256 * 2     # JB_X_WORDS of include/jorldy_b200_fused.h (zeroed before the rendezvous)
 
 
+def exchange_layout(num_flat, world_size):
+    """Float offsets of the regions of one rank's exchange buffer (include/jorldy_b200_fused.h):
+    gradient | owner inbox (LL words) | averaged gradient (LL words) | message words.  An LL word is 64 bits = 2 floats,
+    written in 16-byte pairs: every region starts on a 32-byte boundary (jb_ppo_fused_run rejects anything else)."""
+    if num_flat % 4:
+        raise RuntimeError("flat parameter buffer is not a whole number of float4")
+    q4 = (num_flat // 4 + world_size - 1) // world_size
+    llin, llout = 8 * world_size * q4, 2 * num_flat
+    llout += -llout % 8
+    base = num_flat + (-num_flat % 8)
+    return {"llin_off": base, "gred_off": base + llin, "flag_off": base + llin + llout,
+            "n": base + llin + llout + P2P_FLAG_WORDS}
+
+
 def _try_p2p(agent, world_size):
     """Peer-mapped gradient exchange buffer for the persistent PPO kernel (csrc/ppo_fused.cu): every rank's flat
     gradient lives in a symmetric-memory allocation whose peer pointers the kernel reads and writes over NVLink, so
@@ -36,9 +50,8 @@ def _try_p2p(agent, world_size):
         import torch.distributed._symmetric_memory as symm
         if net.num_flat % 4:
             raise RuntimeError("flat parameter buffer is not a whole number of float4")
-        q4 = (net.num_flat // 4 + world_size - 1) // world_size
-        llin, llout = 8 * world_size * q4, 2 * net.num_flat          # 64-bit LL words, counted in floats
-        n = net.num_flat + llin + llout + P2P_FLAG_WORDS             # gradient | owner inbox | averaged gradient | message words
+        lay = exchange_layout(net.num_flat, world_size)
+        n = lay["n"]
         buf = symm.empty(n, dtype=torch.float32, device=net.flat.device)
         buf.zero_()
         torch.cuda.synchronize()
@@ -70,7 +83,7 @@ def _try_p2p(agent, world_size):
     net.rebind_grad(buf)
     dist.barrier()
     agent.p2p = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "rank": dist.get_rank(), "world": world_size, "epoch": 0,
-                 "llin_off": net.num_flat, "gred_off": net.num_flat + llin, "flag_off": net.num_flat + llin + llout}
+                 "llin_off": lay["llin_off"], "gred_off": lay["gred_off"], "flag_off": lay["flag_off"]}
 
 
 def attach(agent, world_size, average_with="avg"):

@@ -35,7 +35,7 @@ def trio(**kw):
 def learn3(agents, ro):
     out = []
     for ag in agents:
-        ro.t = 32
+        ro.t = ag.n_step
         torch.manual_seed(1234)
         out.append(ag.learn_rollout(ro))
         torch.cuda.synchronize()
@@ -82,6 +82,25 @@ assert torch.equal(flat, ref), "weights diverged across ranks"
 obs0 = env.obs.clone(); o0 = obs0.clone(); dist.broadcast(o0, src=0)
 assert rank == 0 or not torch.equal(obs0, o0), "ranks should own different env shards"
 print(f"rank {rank}: PPO dp ok (fused path: {bool(agent._fused)})", {k: round(v, 4) for k, v in res.items()}, flush=True)
+# ---- PPO dp, continuous policy (obs 11 / act 3: a flat parameter buffer that is NOT a multiple of 8 floats) ----
+envc = Env("hopper", num_envs=64, seed=2, id=rank, device=dev)
+mkc = lambda **k2: Agent("ppo", state_size=11, action_size=3, hidden_size=512, batch_size=256, n_step=16, n_epoch=1, device=dev,
+                         network="continuous_policy_value", run_step=10**6, seed=300 + rank, epsilon_clip=1e9,
+                         optim_config={"name": "adam", "lr": 3e-4}, **k2)
+ac, rc_ = mkc(), mkc(use_fused=False)
+ac.rng_stream_base = rank << 32
+parallel.attach(ac, world)
+parallel.attach(rc_, world); rc_.p2p = None
+rc_.network.load_state_dict(ac.network.state_dict())
+assert (ac.p2p is not None) == (agent.p2p is not None), "the continuous network must get the same exchange path as the discrete one"
+roc = RolloutCollector(envc, ac).collect()
+resc, resr = learn3((ac, rc_), roc)
+dc = (ac.network.flat - rc_.network.flat).abs().max().item()
+fc = ac.network.flat.clone(); f0 = fc.clone(); dist.broadcast(f0, src=0)
+assert torch.equal(fc, f0), "continuous PPO weights diverged across ranks"
+assert dc < 5e-5, dc
+print(f"rank {rank}: PPO continuous dp ok (p2p={bool(ac.p2p)}, num_flat % 8 = {ac.network.num_flat % 8}): fused vs graph+NCCL max|dW| = {dc:.3e} "
+      f"after {64 * 16 // 256} steps", flush=True)
 # ---- Ape-X sharded PER ----
 env2 = Env("cartpole", num_envs=64, seed=1, id=rank, device=dev)
 ax = Agent("ape_x", state_size=4, action_size=2, hidden_size=128, network="dueling", buffer_size=8192, batch_size=64,

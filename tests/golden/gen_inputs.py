@@ -204,3 +204,61 @@ Q_CASES = {
     "rainbow_h512": dict(_QBASE, seed=31, agent="rainbow", net="rainbow", H=512, B=32, A=2, K=51, v_min=-1, v_max=10,
                          n_step=3, alpha=0.5, lr=6.25e-5),
 }
+
+
+# ---- continuous off-policy family (DDPG / TD3 / SAC) -------------------------------------------------------------------
+def ac_shapes(case, which):
+    """which: "actor" | "critic" — state_dict key order of policy.py:8-56 / q_network.py:23-40."""
+    from collections import OrderedDict
+    H, D, A = case["H"], case["D"], case["A"]
+    s = OrderedDict()
+    s["head.l.weight"] = (H, D); s["head.l.bias"] = (H,)
+    if which == "critic":
+        s["e.weight"] = (H, A); s["e.bias"] = (H,)
+        s["l.weight"] = (H, 2 * H); s["l.bias"] = (H,)
+        s["q.weight"] = (1, H); s["q.bias"] = (1,)
+    else:
+        s["l.weight"] = (H, H); s["l.bias"] = (H,)
+        if case["agent"] == "sac":
+            s["mu.weight"] = (A, H); s["mu.bias"] = (A,)
+            s["log_std.weight"] = (A, H); s["log_std.bias"] = (A,)
+        else:
+            s["pi.weight"] = (A, H); s["pi.bias"] = (A,)
+    return s
+
+
+AC_NETS = ("actor", "critic1", "critic2", "target_actor", "target_critic1", "target_critic2")
+
+
+def ac_params(case, net):
+    """Seeded parameters of one of AC_NETS (targets get their own seeds: the learners must not assume target == online)."""
+    which = "actor" if "actor" in net else "critic"
+    return make_params(ac_shapes(case, which), case["seed"] + 100 * (1 + AC_NETS.index(net)))
+
+
+def ac_case_inputs(case):
+    rs = np.random.RandomState(case["seed"] + 5)
+    B, D, A, n = case["B"], case["D"], case["A"], case.get("n_learns", 1)
+    out = dict(state=(0.7 * rs.standard_normal((B, D))).astype(np.float32),
+               next_state=(0.7 * rs.standard_normal((B, D))).astype(np.float32),
+               action=np.tanh(rs.standard_normal((B, A))).astype(np.float32),
+               reward=rs.choice([0.1, -1.0, 1.0, 2.5], size=(B, 1)).astype(np.float64),
+               done=rs.uniform(size=(B, 1)) < 0.2)
+    # one set of normal draws per learn(): TD3 target smoothing / SAC next-state and actor reparameterisation noise
+    out["noise"] = [{"target": rs.standard_normal((B, A)).astype(np.float32),
+                     "next": rs.standard_normal((B, A)).astype(np.float32),
+                     "actor": rs.standard_normal((B, A)).astype(np.float32)} for _ in range(n)]
+    return out
+
+
+_ACBASE = dict(D=3, A=1, H=64, B=16, gamma=0.99, actor_lr=5e-4, critic_lr=1e-3, alpha_lr=3e-4, tau=5e-3)
+AC_CASES = {
+    "ddpg_small": dict(_ACBASE, seed=41, agent="ddpg"),
+    "ddpg_h512": dict(_ACBASE, seed=42, agent="ddpg", D=11, A=3, H=512, B=128),
+    "td3_first": dict(_ACBASE, seed=43, agent="td3", A=2, num_learn=0),       # actor update, no soft update (num_learn == 0)
+    "td3_skip": dict(_ACBASE, seed=44, agent="td3", A=2, num_learn=1),        # critics only
+    "td3_delayed": dict(_ACBASE, seed=45, agent="td3", D=11, A=3, num_learn=2),   # actor + soft update of the three targets
+    "sac_static": dict(_ACBASE, seed=46, agent="sac", A=2, dynamic_alpha=False),
+    "sac_dynamic": dict(_ACBASE, seed=47, agent="sac", D=11, A=3, dynamic_alpha=True, n_learns=2),   # two learns: alpha lags
+    "sac_h512": dict(_ACBASE, seed=48, agent="sac", D=11, A=3, H=512, B=64, dynamic_alpha=True),
+}

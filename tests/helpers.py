@@ -75,3 +75,43 @@ def run_q_oracle(case):
     if case["agent"] in ("c51", "rainbow"):
         return odqn.dist_learn(params, tparams, batch, hp, optim), inp
     return odqn.td_learn(params, tparams, batch, hp, optim), inp
+
+
+# ---- continuous off-policy family ----------------------------------------------------------------------------------------
+def ac_oracle_inputs(case):
+    inp = G.ac_case_inputs(case)
+    nets = {n: {k: torch.from_numpy(v) for k, v in G.ac_params(case, n).items()} for n in G.AC_NETS}
+    batch = {"state": torch.from_numpy(inp["state"]), "next_state": torch.from_numpy(inp["next_state"]),
+             "action": torch.from_numpy(inp["action"]), "reward": torch.from_numpy(inp["reward"].astype(np.float32)),
+             "done": torch.from_numpy(inp["done"].astype(np.float32))}
+    noise = [{k: torch.from_numpy(v) for k, v in nz.items()} for nz in inp["noise"]]
+    return nets, batch, noise
+
+
+def run_ac_oracle(case):
+    """Runs the case's learn() calls on the CPU oracle; returns (list of per-learn outputs, final network dict)."""
+    from oracle import actor_critic as oac
+    nets, batch, noise = ac_oracle_inputs(case)
+    ag, outs, opt_state = case["agent"], [], None
+    hp = {k: case[k] for k in ("gamma", "tau", "actor_lr", "critic_lr", "alpha_lr")}
+    if ag == "sac":
+        log_alpha = torch.zeros(1) if case["dynamic_alpha"] else torch.tensor(-2.0)
+        alpha = log_alpha.exp()
+        hp.update(use_dynamic_alpha=case["dynamic_alpha"], target_entropy=-case["A"])
+    for i, nz in enumerate(noise):
+        if ag == "ddpg":
+            o = oac.ddpg_learn(nets["actor"], nets["critic1"], nets["target_actor"], nets["target_critic1"], batch, hp, opt_state)
+            nets.update(actor=o["actor"], critic1=o["critic"])
+        elif ag == "td3":
+            hp.update(update_delay=2, target_noise_std=0.2, target_noise_clip=0.5)
+            o = oac.td3_learn(nets["actor"], nets["critic1"], nets["critic2"], nets["target_actor"], nets["target_critic1"],
+                              nets["target_critic2"], batch, hp, nz["target"], case["num_learn"] + i, opt_state)
+            nets.update({k: o[k] for k in G.AC_NETS})
+        else:
+            o = oac.sac_learn(nets["actor"], nets["critic1"], nets["critic2"], nets["target_critic1"], nets["target_critic2"],
+                              log_alpha, alpha, batch, hp, nz["next"], nz["actor"], opt_state)
+            nets.update(actor=o["actor"], critic1=o["critic1"], critic2=o["critic2"])
+            log_alpha, alpha = o["log_alpha"], o["alpha"]
+        opt_state = o["opt_state"]
+        outs.append(o)
+    return outs, nets

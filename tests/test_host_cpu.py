@@ -133,3 +133,28 @@ def test_parallel_attach_gloo_world2(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_exchange_layout_satisfies_the_kernel_checks():
+    """jb_ppo_fused_run (csrc/ppo_fused.cu) rejects an exchange buffer whose regions are not 32-byte aligned or overlap;
+    the PPO obs-11/act-3 network (num_flat % 8 == 4) was the case that tripped it."""
+    from jorldy_b200.core.parallel import exchange_layout, P2P_FLAG_WORDS
+
+    def num_flat(shapes):
+        return sum((int(np.prod(s)) + 3) // 4 * 4 for s in shapes)
+
+    H = 512
+    nets = {"cartpole": [(H, 4), (H,), (H, H), (H,), (2, H), (2,), (1, H), (1,)],
+            "hopper": [(H, 11), (H,), (H, H), (H,), (3, H), (3,), (3, H), (3,), (1, H), (1,)],
+            "tiny": [(32, 3), (32,), (32, 32), (32,), (1, 32), (1,)]}
+    for name, shapes in nets.items():
+        nf = num_flat(shapes)
+        for world in (2, 3, 4, 8):
+            lay = exchange_layout(nf, world)
+            P4 = nf // 4
+            q4 = (P4 + world - 1) // world
+            assert lay["llin_off"] >= P4 * 4, name
+            assert lay["gred_off"] >= lay["llin_off"] + 8 * world * q4, name
+            assert lay["flag_off"] >= lay["gred_off"] + 8 * P4, name
+            assert lay["llin_off"] % 8 == 0 and lay["gred_off"] % 8 == 0 and lay["flag_off"] % 4 == 0, (name, world, lay)
+            assert lay["n"] == lay["flag_off"] + P2P_FLAG_WORDS

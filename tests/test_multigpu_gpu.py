@@ -2,7 +2,7 @@
 boxes with fewer than 2 GPUs.  Spawns scripts/multigpu_check.py under torchrun: the persistent kernel's
 reduce-scatter + all-gather over peer memory equals the CUDA-graph + NCCL all-reduce path to 2e-5 after 8 minibatch
 steps, weights stay bit-identical across ranks over 3 more learn() calls, Ape-X's sharded PER keeps the global
-max-weight normalisation."""
+max-weight normalisation; the continuous-policy network (flat buffer not a multiple of 8 floats) takes the same exchange."""
 import os
 import subprocess
 import sys
@@ -24,3 +24,4 @@ def test_in_kernel_exchange_two_ranks():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "in-kernel gradient exchange ON" in r.stdout
     assert r.stdout.count("PPO dp ok") == 2 and r.stdout.count("Ape-X sharded PER ok") == 2
+    assert r.stdout.count("PPO continuous dp ok (p2p=True") == 2          # the obs-11 / act-3 network: num_flat % 8 == 4
