@@ -54,5 +54,39 @@ def main():
         print(tag, "saved", {k: v.shape for k, v in out.items()})
 
 
+AC_CASES = {
+    "ddpg": dict(state_size=3, action_size=2, hidden_size=64, buffer_size=64, batch_size=8),
+    "td3": dict(state_size=3, action_size=2, hidden_size=64, buffer_size=64, batch_size=8),
+    "sac": dict(state_size=3, action_size=2, hidden_size=64, buffer_size=64, batch_size=8, use_dynamic_alpha=True),
+}
+
+
+def main_ac():
+    """DDPG / TD3 / SAC: two learn() calls (every optimiser has state), then save + the agents' own eval outputs."""
+    rs = np.random.RandomState(1)
+    for tag, kw in AC_CASES.items():
+        agent = Agent(tag, device="cuda", run_step=100, seed=3, start_train_step=1, **kw)
+        s = (0.7 * rs.standard_normal((16, 3))).astype(np.float32)
+        a = np.tanh(rs.standard_normal((16, 2))).astype(np.float32)
+        tr = {"state": s, "next_state": s[::-1].copy(), "reward": rs.standard_normal((16, 1)), "done": rs.uniform(size=(16, 1)) < 0.2,
+              "action": a}
+        for step in (1, 2):
+            agent.process([tr], step)
+        assert agent.num_learn == 2
+        d = os.path.join(OUT, tag)
+        os.makedirs(d, exist_ok=True)
+        agent.save(d)
+        sd, ad = torch.from_numpy(s).cuda(), torch.from_numpy(a).cuda()
+        out = {"state": s, "action": a, "action_eval": agent.act(s, training=False)["action"]}
+        for i, c in enumerate(agent.critics):
+            out[f"q{i + 1}"] = c.forward(sd, ad, tag="fx.").cpu().numpy().copy()
+        if tag == "sac":
+            out["log_alpha"] = agent.log_alpha.flat[:1].cpu().numpy()
+        np.savez_compressed(os.path.join(d, "outputs.npz"), **out)
+        print(tag, "saved", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if "--ac-only" not in sys.argv:
+        main()
+    main_ac()

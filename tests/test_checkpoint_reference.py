@@ -68,3 +68,37 @@ def test_reference_loads_b200_checkpoint(agent_mod, tag):
     # optimizer state came along (one step taken before saving)
     st = agent.optimizer.state_dict()["state"]
     assert len(st) == len(list(agent.network.parameters()))
+
+
+AC_CASES = {
+    "ddpg": dict(state_size=3, action_size=2, hidden_size=64, buffer_size=64, batch_size=8),
+    "td3": dict(state_size=3, action_size=2, hidden_size=64, buffer_size=64, batch_size=8),
+    "sac": dict(state_size=3, action_size=2, hidden_size=64, buffer_size=64, batch_size=8, use_dynamic_alpha=True),
+}
+
+
+@pytest.mark.parametrize("tag", list(AC_CASES))
+def test_reference_loads_b200_actor_critic_checkpoint(agent_mod, tag):
+    """ddpg.py:186-197 / td3.py:232-246 / sac.py:321-339 load() on a checkpoint written by the B200 agent after two learns."""
+    d = os.path.join(CKPT, tag)
+    if not os.path.exists(os.path.join(d, "ckpt")):
+        pytest.skip(f"no checkpoint fixture for {tag}")
+    agent = agent_mod.Agent(tag, device="cpu", run_step=100, **AC_CASES[tag])
+    agent.load(d)
+    exp = dict(np.load(os.path.join(d, "outputs.npz")))
+    x, a = torch.from_numpy(exp["state"]), torch.from_numpy(exp["action"])
+    act = agent.act(exp["state"], training=False)["action"]
+    np.testing.assert_allclose(act, exp["action_eval"], rtol=0, atol=2e-6)
+    with torch.no_grad():
+        if tag == "ddpg":
+            np.testing.assert_allclose(agent.critic(x, a).numpy(), exp["q1"], rtol=2e-5, atol=2e-6)
+        else:       # the reference's load() puts critic2's weights into critic1 and never loads critic2
+            np.testing.assert_allclose(agent.critic1(x, a).numpy(), exp["q2"], rtol=2e-5, atol=2e-6)
+    opts = [agent.actor_optimizer] + ([agent.critic_optimizer] if tag == "ddpg" else [agent.critic_optimizer1, agent.critic_optimizer2])
+    for i, o in enumerate(opts):
+        st = o.state_dict()["state"]
+        steps = 1.0 if (tag == "td3" and i == 0) else 2.0          # TD3's actor steps on every second learn (td3.py:174)
+        assert len(st) == len(o.param_groups[0]["params"]) and all(float(v["step"]) == steps for v in st.values())
+    if tag == "sac":
+        np.testing.assert_allclose(agent.log_alpha.detach().numpy(), exp["log_alpha"], rtol=0, atol=0)
+        assert float(agent.alpha_optimizer.state_dict()["state"][0]["step"]) == 2.0
