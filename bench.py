@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
-CONFIGS = ("ppo_cartpole", "ppo_continuous", "rainbow_frames", "apex")
+CONFIGS = ("ppo_cartpole", "ppo_continuous", "rainbow_frames", "apex", "sac_hopper")
 
 
 def parse():
@@ -667,7 +667,209 @@ class ReplayWorkload:
                 "torch-CPU oracle port of run_mode.py:68-91")
 
 
+# ================================================================================================
+# the continuous off-policy family, measured on SAC (config/sac/mujoco.py) over the Hopper-dimension task
+# ================================================================================================
+class ACWorkload:
+    """Not a BASELINE.json configuration: the measurement of the section-8f "next" row.  N batched actors step the
+    synthetic obs-11 / act-3 task; every `update_period` steps of every actor the learner runs ONE SAC.learn() (the
+    reference's sync loop, run_mode.py:180-187).  1024 actors x 2 steps = 2048 transitions per learn() — the data : update
+    ratio of config/sac/mujoco.py's distributed setting (16 workers x update_period 128)."""
+
+    def __init__(self, name, args, world):
+        self.name, self.world = name, world
+        self.D, self.A, self.H = 11, 3, 512
+        self.n_actors, self.buffer, self.B, self.update_period = 1024, 1_000_000, 256, 2
+        self.scaling = "weak"
+        self.optim = {"actor": "adam", "critic": "adam", "alpha": "adam", "actor_lr": 5e-4, "critic_lr": 1e-3, "alpha_lr": 3e-4}
+        self.override = any(v is not None for v in (args.n_envs, args.batch, args.buffer, args.rounds))
+        self.n_actors = args.n_envs or self.n_actors
+        self.B = args.batch or self.B
+        self.buffer = args.buffer or self.buffer
+        self.rounds = args.rounds or 64
+        self.launch_estimate = None
+
+    def config(self):
+        c = {"workload": (f"SAC (dynamic alpha, twin critics, MLP 11-512-512, A=3) on the synthetic Hopper-dimension task, {self.n_actors} batched "
+                          f"actors/GPU, {self.buffer}-slot HBM replay, B={self.B}, one learn() per {self.update_period} steps of every actor "
+                          f"(config.sac.mujoco hyper-parameters; start_train_step shortened to the prefill; buffer enlarged from 50 000 to "
+                          f"hold the batched actors' stream)"),
+             "config_name": self.name, "n_actors_per_gpu": self.n_actors, "buffer_slots_per_gpu": self.buffer, "batch_size_per_gpu": self.B,
+             "update_period": self.update_period, "rounds_per_step": self.rounds, "parallelism": f"replicas x{self.world}",
+             "gradient_exchange": "none (independent replicas)",
+             "l2": "256 MB fill between steps; every learn() gathers a fresh minibatch from the replay"}
+        if self.override:
+            c["override"] = True
+        return c
+
+    def reference_sample(self):
+        return ("ONE actor (batch-1 policy forward, numpy env) x 128 steps then one SAC.learn() (B=256) per round on the host cores "
+                "(config/sac/mujoco.py update_period 128): a BOUNDED SAMPLE of the configuration named in `config`, not the same actor count")
+
+    def _agent(self, Agent, dev, seed, n_total):
+        return Agent("sac", state_size=self.D, action_size=self.A, hidden_size=self.H, optim_config=dict(self.optim),
+                     use_dynamic_alpha=True, gamma=0.99, tau=5e-3, buffer_size=self.buffer, batch_size=self.B, start_train_step=0,
+                     run_step=10 ** 8, lr_decay=True, device=dev, seed=seed)
+
+    def build(self, torch, dev, rank):
+        from jorldy_b200.core import Agent, Env
+        from jorldy_b200.core.collect import ReplayCollector
+        self.torch, self.dev, self.rank = torch, dev, rank
+        self.env = Env("hopper", num_envs=self.n_actors, seed=0, id=rank, device=dev)
+        self.agent = self._agent(Agent, dev, 1234 + rank, self.n_actors)
+        self.agent.rng_stream_base = rank << 32
+        self.rc = ReplayCollector(self.env, self.agent, self.update_period)
+        self.l2_flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+        self.step_no = 0
+        while self.agent.memory.size < max(4 * self.B, 4096):
+            self.step_no, _ = self.rc.run_round(self.step_no)
+        # launches of OUR kernels per round, counted from the code path: per env step 3 (actor forward) + 1 (sample) + 1 (env) + 5
+        # (replay row stores); per learn() 5 (gather) + 78 (forwards, losses, backwards, 4 Adam steps, soft updates, noise fills)
+        self.launch_estimate = self.rounds * (10 * self.update_period + 83)
+
+    def step(self):
+        self.l2_flush.fill_(float(self.step_no))
+        res = {}
+        for _ in range(self.rounds):
+            self.step_no, r = self.rc.run_round(self.step_no)
+            res = r or res
+        return res
+
+    def env_steps_per_step(self):
+        return self.n_actors * self.update_period * self.rounds * self.world
+
+    def learner_transitions_per_step(self):
+        return self.B * self.world * self.rounds
+
+    def launches_per_step(self):
+        return self.launch_estimate
+
+    def teardown(self):
+        pass
+
+    def extra(self):
+        return None
+
+    def roofline(self, peaks):
+        """One learn() timed alone: 4 actor-forward equivalents (2 forwards + backward) and 12 critic-forward equivalents
+        (2 online + 2 target + 2 on the actor's action, 2 full backwards = 4, 2 input-gradient-only backwards = 2)."""
+        torch, agent = self.torch, self.agent
+        times = []
+        for i in range(13):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(); agent.learn(); a1.record(); torch.cuda.synchronize()
+            if i >= 3:
+                times.append(a0.elapsed_time(a1))
+        ms = sum(times) / len(times)
+        D, A, H = self.D, self.A, self.H
+        actor = 2.0 * (D * H + H * H + H * 2 * A)
+        critic = 2.0 * (D * H + A * H + 2 * H * H + H)
+        flops = self.B * (4 * actor + 12 * critic)
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = flops / (ms * 1e-3) / 1e12
+        return {"kernel": "SAC.learn() of one minibatch: fp32 FFMA tile GEMMs (csrc/linear.cu) + the row kernels of csrc/actor_critic.cu",
+                "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
+                "algorithmic_flops_per_launch": flops, "ms_per_learn": ms, "learner_transitions_per_sec_learn_only": self.B / (ms * 1e-3),
+                "world": self.world, "note": f"latency-bound at B={self.B}: ~83 launches of 0.1-0.5 GFLOP each per learn(), eager (no CUDA graph)"}
+
+    def e2e(self, np, steps=1):
+        from jorldy_b200.core import Agent, Env
+        torch, dev, rank = self.torch, self.dev, self.rank
+        N, rounds = self.n_actors, max(1, self.rounds // 4)
+        env = Env("hopper", num_envs=N, seed=1, id=rank, device=dev)
+        agent = self._agent(Agent, dev, 99 + rank, N)
+        state = env.reset()
+        cnt = {"h2d": 0, "d2h": 0, "step": 0}
+
+        def one_round():
+            nonlocal state
+            batch = []
+            for _ in range(self.update_period):
+                ad = agent.act(state, True)                                   # H2D state, D2H action
+                ns, r, d = env.step(ad["action"])                             # H2D action, D2H (ns, r, d)
+                batch.append({"state": state, "action": ad["action"], "reward": r, "done": d, "next_state": ns})
+                cnt["h2d"] += state.nbytes + ad["action"].nbytes
+                cnt["d2h"] += ad["action"].nbytes + ns.nbytes + 8 * N
+                state = env.obs.cpu().numpy()                                 # post-auto-reset observation
+                cnt["d2h"] += state.nbytes
+                cnt["step"] += 1
+            agent.process(batch, cnt["step"])                                 # H2D the transitions, learn(), D2H the stats
+            cnt["h2d"] += sum(v.nbytes for tr in batch for v in tr.values())
+            cnt["d2h"] += 40
+
+        while agent.memory.size < 2 * self.B:
+            one_round()
+        torch.cuda.synchronize()
+        cnt["h2d"] = cnt["d2h"] = 0
+        t0 = time.perf_counter()
+        for _ in range(steps * rounds):
+            one_round()
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        scale = self.rounds / rounds
+        return {"value": self.world * N * self.update_period * rounds * steps / sec, "unit": UNIT,
+                "h2d_bytes_per_step": int(self.world * cnt["h2d"] / steps * scale), "d2h_bytes_per_step": int(self.world * cnt["d2h"] / steps * scale),
+                "ms_per_step": 1e3 * sec / steps * scale, "rounds_timed": rounds * steps,
+                "api": "Agent.act / Env.step / Agent.process (numpy, pageable host memory)"}
+
+    def cpu_run(self, n_workers, n_rollouts, threads):
+        """run_mode.py:180-198 around the oracle: one actor collects 128 transitions with batch-1 policy forwards, then one
+        SAC.learn() (sac.py:162-260) on a uniform minibatch of the python-list replay."""
+        import numpy as np
+        import torch
+        from oracle import actor_critic as oac
+        from oracle.classic_control import SyntheticControlBatch
+        from jorldy_b200.core.env.synth import synth_weights
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import gen_inputs as G
+        torch.set_num_threads(threads)
+        case = dict(D=self.D, A=self.A, H=self.H, agent="sac", seed=7)
+        nets = {n: {k: torch.from_numpy(v) for k, v in G.ac_params(case, n).items()} for n in ("actor", "critic1", "critic2")}
+        nets["target_critic1"] = {k: v.clone() for k, v in nets["critic1"].items()}
+        nets["target_critic2"] = {k: v.clone() for k, v in nets["critic2"].items()}
+        Ws, Wa = synth_weights(self.D, self.A, 0)
+        env = SyntheticControlBatch(1, self.D, self.A, seed=0, stream_base=0, auto_reset=False, Ws=Ws, Wa=Wa)
+        state = env.reset()
+        hp = {"gamma": 0.99, "tau": 5e-3, "actor_lr": 5e-4, "critic_lr": 1e-3, "alpha_lr": 3e-4, "use_dynamic_alpha": True,
+              "target_entropy": -self.A}
+        log_alpha = torch.zeros(1)
+        alpha = log_alpha.exp()
+        ring, opt_state, rs = [], None, np.random.RandomState(0)
+        n_rounds = 8 * n_rollouts
+        t0, env_steps = None, 0
+        for rnd in range(n_rounds + 2):                              # 2 untimed rounds fill the replay past one batch
+            if rnd == 2:
+                t0, env_steps = time.perf_counter(), 0
+            for _t in range(128):
+                with torch.no_grad():
+                    mu, std = oac.continuous_policy(nets["actor"], torch.from_numpy(state))
+                    a = torch.tanh(torch.normal(mu, std)).numpy()
+                ns, r, d = env.step(a)
+                ring.append((state, a.astype(np.float32), np.asarray(r, np.float32).reshape(1, 1), ns, np.asarray(d, np.float32).reshape(1, 1)))
+                state = env.reset() if d[0] else ns
+                env_steps += 1
+            if rnd < 1:
+                continue
+            idx = rs.randint(len(ring), size=self.B)
+            cols = list(zip(*[ring[i] for i in idx]))
+            batch = {k: torch.from_numpy(np.concatenate(c)) for k, c in zip(("state", "action", "reward", "next_state", "done"), cols)}
+            o = oac.sac_learn(nets["actor"], nets["critic1"], nets["critic2"], nets["target_critic1"], nets["target_critic2"], log_alpha,
+                              alpha, batch, hp, torch.randn(self.B, self.A), torch.randn(self.B, self.A), opt_state)
+            nets.update(actor=o["actor"], critic1=o["critic1"], critic2=o["critic2"])
+            nets["target_critic1"] = oac.soft_update(nets["target_critic1"], o["critic1"], hp["tau"])
+            nets["target_critic2"] = oac.soft_update(nets["target_critic2"], o["critic2"], hp["tau"])
+            log_alpha, alpha, opt_state = o["log_alpha"], o["alpha"], o["opt_state"]
+        return env_steps, time.perf_counter() - t0
+
+    def cpu_sample_text(self, n_rollouts):
+        return (f"1 actor x {128 * 8 * n_rollouts} env steps (batch-1 policy forward, numpy synthetic env) + one SAC.learn() (B={self.B}) per 128 steps, "
+                "torch-CPU oracle port of run_mode.py:180-198")
+
+
 def make_workload(name, args, world):
+    if name == "sac_hopper":
+        return ACWorkload(name, args, world)
     return PPOWorkload(name, args, world) if name.startswith("ppo") else ReplayWorkload(name, args, world)
 
 
