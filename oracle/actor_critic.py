@@ -175,3 +175,32 @@ def sac_learn(actor, critic1, critic2, t_critic1, t_critic2, log_alpha, alpha, b
             "result": {"critic_loss1": loss1.item(), "critic_loss2": loss2.item(), "actor_loss": actor_loss.item(),
                        "alpha_loss": alpha_loss.item(), "max_Q": float(max_Q), "mean_Q": min_q.mean().item(),
                        "alpha": new_alpha.item(), "entropy": entropy.mean().item()}}
+
+
+# ---- act() arithmetic (pinned by tests/golden/act_{ddpg,td3,sac}.npz) ---------------------------------------------------
+def act_ddpg(actor, state, X, normal, mu, theta, sigma, training=True):
+    """ddpg.py:113-118 for ONE actor (state (1, D), OU state X (1, A)): returns (action, new X).  The reference's action is
+    float64 (float32 mu + float64 clipped OU state)."""
+    with torch.no_grad():
+        m = deterministic_policy(actor, torch.as_tensor(state, dtype=torch.float32)).numpy()
+    if not training:
+        return m, X
+    X = ou_step(X, mu, theta, sigma, normal)
+    return m + X.clip(-1.0, 1.0), X
+
+
+def act_td3(actor, state, normal, action_noise_std, training=True):
+    """td3.py:137-143: clip(actor(s) + N(0, std), -1, 1); `normal` = standard draws of shape (A,)."""
+    with torch.no_grad():
+        a = deterministic_policy(actor, torch.as_tensor(state, dtype=torch.float32)).numpy()
+    if training:
+        a = (a + action_noise_std * np.asarray(normal, dtype=np.float64)).clip(-1.0, 1.0)
+    return a
+
+
+def act_sac(actor, state, eps, training=True):
+    """sac.py:139-142: tanh(Normal(mu, std).sample()) = tanh(mu + std * eps); tanh(mu) when not training."""
+    with torch.no_grad():
+        mu, std = continuous_policy(actor, torch.as_tensor(state, dtype=torch.float32))
+        z = mu + std * torch.as_tensor(eps, dtype=torch.float32) if training else mu
+        return torch.tanh(z).numpy()
