@@ -771,7 +771,9 @@ class ACWorkload:
                 "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
                 "algorithmic_flops_per_launch": flops, "ms_per_learn": ms, "learner_transitions_per_sec_learn_only": self.B / (ms * 1e-3),
-                "world": self.world, "note": f"latency-bound at B={self.B}: ~83 launches of 0.1-0.5 GFLOP each per learn(), eager (no CUDA graph)"}
+                "world": self.world, "cuda_graph": bool(agent._graphs),
+                "note": f"latency-bound at B={self.B}: ~83 kernels of <= 0.5 GFLOP each per learn(), "
+                        + ("replayed as one CUDA graph" if agent._graphs else "launched eagerly")}
 
     def e2e(self, np, steps=1):
         from jorldy_b200.core import Agent, Env

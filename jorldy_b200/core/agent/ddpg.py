@@ -37,8 +37,10 @@ class _ActorCritic(BaseAgent):
     _n_critics = 1
 
     def _common(self, state_size, action_size, hidden_size, actor, critic, head, optim_config, gamma, buffer_size, batch_size,
-                start_train_step, tau, run_step, lr_decay, device, seed, target_actor):
+                start_train_step, tau, run_step, lr_decay, device, seed, target_actor, use_cuda_graph=True):
         self.device = require_cuda(device)
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graphs, self._warm, self._idx_buf = {}, set(), None
         self.state_size, self.action_size = state_size, action_size
         self.seed = int(seed)
         mk = lambda name: Network(name, state_size, action_size, D_hidden=hidden_size, head=head, device=self.device)
@@ -71,6 +73,9 @@ class _ActorCritic(BaseAgent):
     # ---- plumbing ----------------------------------------------------------------------------------------------------
     def _optimizers(self):
         return [self.actor_optimizer] + self.critic_optimizers
+
+    def _all_optimizers(self):
+        return self._optimizers()
 
     def _fill(self, key, shape, purpose, kind=0, lo=0.0, hi=1.0):
         """Standard normals (kind 0) / uniforms in [lo, hi) (kind 1) from the device Philox stream of this agent."""
@@ -122,8 +127,41 @@ class _ActorCritic(BaseAgent):
         action, _ = self.act_device(self._net_input(self._state_to_device(state)), training)
         return {"action": action.cpu().numpy()}
 
+    def _learn_batch(self, batch):
+        """One eager learn() on a device batch (the parity tests call this with injected draws)."""
+        self._learn_core(batch)
+        return self._finish()
+
+    def _variant(self):
+        """Host-side state that changes WHICH kernels a learn() launches (TD3's delayed actor / target updates)."""
+        return 0
+
     def learn(self):
-        return self._learn_batch(self._sample())
+        """replay gather + _learn_core as ONE CUDA-graph replay (~90 launches otherwise).  The first learn of every variant runs
+        eagerly (it allocates the workspaces and is a real learn), the second captures, later ones replay; the minibatch indices
+        travel through a static device buffer, lr / Adam step / Philox counters live in device memory."""
+        if not self.use_cuda_graph or self._inject_noise is not None:
+            return self._learn_batch(self._sample())
+        B = self.batch_size
+        if self._idx_buf is None:
+            self._idx_buf = torch.zeros(B, dtype=torch.int64, device=self.device)
+        src = self._inject_idx if self._inject_idx is not None else self.memory.sample_indices(B)
+        self._idx_buf.copy_(torch.as_tensor(np.asarray(src), dtype=torch.int64))
+        for opt in self._all_optimizers():
+            opt._sync_lr()                       # graph replays do not pass through optimizer.step()'s host-side lr check
+        key = self._variant()
+        if key not in self._warm:
+            self._warm.add(key)
+            self._learn_core(self.memory.gather_device(self._idx_buf))
+        else:
+            g = self._graphs.get(key)
+            if g is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):        # capture does not execute
+                    self._learn_core(self.memory.gather_device(self._idx_buf))
+                self._graphs[key] = g
+            g.replay()
+        return self._finish()
 
     # ---- checkpoints: the reference's key layout (ddpg.py:176-197, td3.py:222-246, sac.py:306-339) ---------------------
     @staticmethod
@@ -178,9 +216,9 @@ class DDPG(_ActorCritic):
     def __init__(self, state_size, action_size, hidden_size=512, actor="deterministic_policy", critic="continuous_q_network",
                  head="mlp", optim_config=_DEFAULT_OPTIM, gamma=0.99, buffer_size=50000, batch_size=128,
                  start_train_step=2000, tau=1e-3, run_step=1e6, lr_decay=True, mu=0, theta=1e-3, sigma=2e-3, device=None,
-                 seed=0, **kwargs):
+                 seed=0, use_cuda_graph=True, **kwargs):
         self._common(state_size, action_size, hidden_size, actor, critic, head, optim_config, gamma, buffer_size, batch_size,
-                     start_train_step, tau, run_step, lr_decay, device, seed, target_actor=True)
+                     start_train_step, tau, run_step, lr_decay, device, seed, target_actor=True, use_cuda_graph=use_cuda_graph)
         self.ou_mu, self.ou_theta, self.ou_sigma = float(mu), float(theta), float(sigma)
         self._ou = {}                    # rows -> OU state X [rows, A] f64 (one process per batched env)
 
@@ -198,7 +236,7 @@ class DDPG(_ActorCritic):
                     self.ou_theta, self.ou_mu, self.ou_sigma, 0 if training else 1, ptr(action), stream_ptr())
         return action, None
 
-    def _learn_batch(self, batch):
+    def _learn_core(self, batch):
         B, s, a, r, d, ns = self._unpack(batch)
         critic, tcritic = self.critics[0], self.target_critics[0]
         na = self._tanh(self.target_actor, self.target_actor.forward_raw(ns, tag="n.", save=False), "n.a")
@@ -209,6 +247,8 @@ class DDPG(_ActorCritic):
                             stream_ptr())
         self._critic_step(0, dq, B)
         self._actor_step(s, B)
+
+    def _finish(self):
         self.num_learn += 1
         st = self._stats[:5].cpu().numpy()
         return {"critic_loss": float(st[0]), "actor_loss": float(st[4]), "max_Q": float(st[2])}
@@ -245,9 +285,10 @@ class TD3(DDPG):
     def __init__(self, state_size, action_size, hidden_size=512, actor="deterministic_policy", critic="continuous_q_network",
                  head="mlp", optim_config=_DEFAULT_OPTIM, gamma=0.99, buffer_size=50000, batch_size=128,
                  start_train_step=2000, initial_random_step=0, tau=1e-3, update_delay=2, action_noise_std=0.1,
-                 target_noise_std=0.2, target_noise_clip=0.5, run_step=1e6, lr_decay=True, device=None, seed=0, **kwargs):
+                 target_noise_std=0.2, target_noise_clip=0.5, run_step=1e6, lr_decay=True, device=None, seed=0,
+                 use_cuda_graph=True, **kwargs):
         self._common(state_size, action_size, hidden_size, actor, critic, head, optim_config, gamma, buffer_size, batch_size,
-                     start_train_step, tau, run_step, lr_decay, device, seed, target_actor=True)
+                     start_train_step, tau, run_step, lr_decay, device, seed, target_actor=True, use_cuda_graph=use_cuda_graph)
         self.initial_random_step, self.num_random_step = initial_random_step, 0
         self.update_delay = update_delay
         self.action_noise_std, self.target_noise_std, self.target_noise_clip = action_noise_std, target_noise_std, target_noise_clip
@@ -268,7 +309,11 @@ class TD3(DDPG):
             noise = self._fill(f"act.n{M}", (M, A), 1)
         return self._tanh(self.actor, pre, "act.a", noise, self.action_noise_std, 0.0, 1.0), None
 
-    def _learn_batch(self, batch):
+    def _variant(self):
+        upd = self.num_learn % self.update_delay == 0
+        return (upd, upd and self.num_learn > 0)         # (actor step, soft target update) — td3.py:174-183
+
+    def _learn_core(self, batch):
         B, s, a, r, d, ns = self._unpack(batch)
         inj = self._inject_noise or {}
         noise = inj.get("target")
@@ -285,11 +330,14 @@ class TD3(DDPG):
                             ptr(self._stats), stream_ptr())
         self._critic_step(0, dq1, B)
         self._critic_step(1, dq2, B)
-        actor_updated = self.num_learn % self.update_delay == 0
+        actor_updated, soft = self._variant()
         if actor_updated:
             self._actor_step(s, B)
-            if self.num_learn > 0:
+            if soft:
                 self.update_target_soft()
+
+    def _finish(self):
+        actor_updated = self.num_learn % self.update_delay == 0
         self.num_learn += 1
         st = self._stats[:5].cpu().numpy()
         if actor_updated:
@@ -313,11 +361,11 @@ class SAC(_ActorCritic):
     def __init__(self, state_size, action_size, hidden_size=512, actor="continuous_policy", critic="continuous_q_network",
                  head="mlp", optim_config=dict(_DEFAULT_OPTIM, alpha="adam", alpha_lr=3e-4), use_dynamic_alpha=False,
                  gamma=0.99, tau=5e-3, buffer_size=50000, batch_size=64, start_train_step=2000, static_log_alpha=-2.0,
-                 target_update_period=10000, run_step=1e6, lr_decay=True, device=None, seed=0, **kwargs):
+                 target_update_period=10000, run_step=1e6, lr_decay=True, device=None, seed=0, use_cuda_graph=True, **kwargs):
         if actor.split("_")[0] != "continuous":
             raise NotImplementedError("only the continuous-action SAC (config/sac/{pendulum,mujoco,...}.py) is built here")
         self._common(state_size, action_size, hidden_size, actor, critic, head, optim_config, gamma, buffer_size, batch_size,
-                     start_train_step, tau, run_step, lr_decay, device, seed, target_actor=False)
+                     start_train_step, tau, run_step, lr_decay, device, seed, target_actor=False, use_cuda_graph=use_cuda_graph)
         self.use_dynamic_alpha = use_dynamic_alpha
         self.log_alpha = _Scalar("log_alpha", 0.0 if use_dynamic_alpha else float(np.float32(static_log_alpha)), self.device)
         self.alpha_optimizer = (Optimizer(optim_config["alpha"], params=self.log_alpha.parameters(), lr=optim_config["alpha_lr"])
@@ -344,7 +392,10 @@ class SAC(_ActorCritic):
         C.jb_sac_sample(ptr(raw), 2 * A, ptr(eps), B, A, ptr(action), ptr(logp), stream_ptr())
         return action, logp
 
-    def _learn_batch(self, batch):
+    def _all_optimizers(self):
+        return self._optimizers() + ([self.alpha_optimizer] if self.use_dynamic_alpha else [])
+
+    def _learn_core(self, batch):
         B, s, a, r, d, ns = self._unpack(batch)
         A, st, sp = self.action_size, self._stats, stream_ptr()
         inj = self._inject_noise or {}
@@ -378,8 +429,10 @@ class SAC(_ActorCritic):
                        st.data_ptr() + 32, sp)
         if self.use_dynamic_alpha:
             self.alpha_optimizer.step()
+
+    def _finish(self):
         self.num_learn += 1
-        h = torch.cat([st[:9], self.alpha]).cpu().numpy()
+        h = torch.cat([self._stats[:9], self.alpha]).cpu().numpy()
         return {"critic_loss1": float(h[0]), "critic_loss2": float(h[1]), "actor_loss": float(h[4]), "alpha_loss": float(h[8]),
                 "max_Q": float(h[2]), "mean_Q": float(h[5]), "alpha": float(h[9]), "entropy": float(h[6])}
 
