@@ -3,7 +3,7 @@
 `load("config.<agent>.<env>")` returns a module-like namespace with the four dicts the reference's
 config modules define (jorldy/config/<agent>/<env>.py: env / agent / optim / train).  Values follow the
 reference's shipped configs for the agents on the north-star path (dqn, double, dueling, multistep,
-per, noisy, c51, rainbow, ape_x, ppo) on cartpole / mountaincar / pendulum / atari(synthetic) /
+per, noisy, c51, rainbow, ape_x, ppo, and ddpg / td3 / sac of SURVEY 8f-4) on cartpole / mountaincar / pendulum / atari(synthetic) /
 mujoco(synthetic dims); an existing JORLDY config directory on sys.path takes precedence
 (manager/config_manager.py).
 """
@@ -90,8 +90,56 @@ def _ppo_config(env):
                 train=dict(_TRAIN_SMALL, eval_iteration=10, distributed_batch_size=256, update_period=128, num_workers=8))
 
 
+# ---- continuous off-policy family: jorldy/config/{ddpg,td3,sac}/{cartpole,pendulum,mujoco}.py --------------------------------
+_TRAIN_MUJOCO = dict(training=True, load_path=None, run_step=1000000, print_period=10000, save_period=100000, eval_iteration=10)
+_AC_ENVS = {"ddpg": ("cartpole", "pendulum", "mujoco"), "td3": ("cartpole", "mujoco"), "sac": ("cartpole", "pendulum", "mujoco")}
+
+
+def _ac_config(agent, env):
+    env_d = {"cartpole": dict(name="cartpole", action_type="continuous", render=False), "pendulum": dict(name="pendulum", render=False),
+             "mujoco": dict(render=False)}[env]
+    mj = env == "mujoco"
+    if agent == "ddpg":
+        a = dict(name="ddpg", actor="deterministic_policy", critic="continuous_q_network", gamma=0.99, buffer_size=50000,
+                 batch_size=128, start_train_step=1000 if mj else 2000, tau=1e-3, lr_decay=True, mu=0, theta=1e-3, sigma=2e-3)
+        opt = dict(actor="adam", critic="adam", actor_lr=5e-4, critic_lr=1e-3)
+        tr = dict(_TRAIN_MUJOCO, distributed_batch_size=256, update_period=1, num_workers=8) if mj else \
+            dict(_TRAIN_SMALL, eval_iteration=10, update_period=1, num_workers=8)
+        if env == "pendulum":
+            tr = dict(_TRAIN_SMALL, eval_iteration=10, distributed_batch_size=128, update_period=1, num_workers=8)
+    elif agent == "td3":
+        a = dict(name="td3", actor="deterministic_policy", critic="continuous_q_network")
+        if mj:
+            a.update(hidden_size=512, gamma=0.99, buffer_size=1000000, batch_size=128, start_train_step=25000,
+                     initial_random_step=25000, tau=5e-3, update_delay=2, action_noise_std=0.1, target_noise_std=0.2,
+                     target_noise_clip=0.5, lr_decay=True)
+            opt = dict(actor="adam", critic="adam", actor_lr=3e-4, critic_lr=3e-4)
+            tr = dict(_TRAIN_MUJOCO, distributed_batch_size=256, update_period=1, num_workers=8)
+        else:       # td3/cartpole.py spells two keys differently from the constructor (actor_period, act_noise_std): kept as shipped
+            a.update(gamma=0.99, buffer_size=50000, batch_size=128, start_train_step=1000, initial_random_step=0, tau=1e-3,
+                     actor_period=2, act_noise_std=0.1, target_noise_std=0.2, target_noise_clip=0.5, lr_decay=True)
+            opt = dict(actor="adam", critic="adam", actor_lr=1e-3, critic_lr=1e-3)
+            tr = dict(_TRAIN_SMALL, eval_iteration=10, update_period=1, num_workers=8)
+    else:
+        a = dict(name="sac", actor="continuous_policy", critic="continuous_q_network", use_dynamic_alpha=True, gamma=0.99, tau=5e-3,
+                 buffer_size=50000, batch_size=256 if mj else 64, start_train_step=25000 if mj else 5000, static_log_alpha=-2.0,
+                 lr_decay=True)
+        if env == "cartpole":
+            a.update(target_update_period=500)
+            a = {k: a[k] for k in ("name", "actor", "critic", "use_dynamic_alpha", "gamma", "tau", "buffer_size", "batch_size",
+                                   "start_train_step", "static_log_alpha", "target_update_period", "lr_decay")}
+        opt = dict(actor="adam", critic="adam", alpha="adam", actor_lr=5e-4, critic_lr=1e-3, alpha_lr=3e-4)
+        if env == "cartpole":
+            opt.update(actor_lr=1.5e-4, critic_lr=3e-4, alpha_lr=1e-5)
+        tr = dict(_TRAIN_MUJOCO, record=False, record_period=500000, update_period=128, num_workers=16) if mj else \
+            dict(_TRAIN_SMALL, eval_iteration=10, update_period=32, num_workers=8)
+    return dict(env=env_d, agent=a, optim=opt, train=tr)
+
+
 def available():
     out = []
+    for ag, envs in _AC_ENVS.items():
+        out += [f"config.{ag}.{e}" for e in envs]
     for ag in list(_VALUE_AGENTS) + ["ape_x"]:
         out += [f"config.{ag}.{e}" for e in ("cartpole", "mountaincar", "atari")]
     out += [f"config.ppo.{e}" for e in ("cartpole", "mountaincar", "pendulum", "mujoco")]
@@ -109,6 +157,8 @@ def load(config_path):
         d = _ape_x_config(env)
     elif agent == "ppo" and env in ("cartpole", "mountaincar", "pendulum", "mujoco"):
         d = _ppo_config(env)
+    elif agent in _AC_ENVS and env in _AC_ENVS[agent]:
+        d = _ac_config(agent, env)
     else:
         raise ImportError(f"no config '{config_path}' (built-ins: {available()})")
     return SimpleNamespace(**d)

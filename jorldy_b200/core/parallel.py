@@ -91,6 +91,13 @@ def attach(agent, world_size, average_with="avg"):
     rank 0) and an averaged flat gradient before every optimiser step."""
     if world_size <= 1:
         return agent
+    if hasattr(agent, "critics"):
+        # DDPG / TD3 / SAC (SURVEY 8f-4): several networks and optimisers per agent, no gradient exchange built for them —
+        # under torchrun every rank is an independent replica (own envs, own replay, own weights), and says so.
+        import warnings
+        warnings.warn(f"{type(agent).__name__}: replicas only (no data-parallel learner for the actor-critic family)")
+        agent.world_size = 1
+        return agent
     dist.broadcast(agent.network.flat, src=0)
     if hasattr(agent, "target_network"):
         dist.broadcast(agent.target_network.flat, src=0)

@@ -158,3 +158,20 @@ def test_exchange_layout_satisfies_the_kernel_checks():
             assert lay["flag_off"] >= lay["gred_off"] + 8 * P4, name
             assert lay["llin_off"] % 8 == 0 and lay["gred_off"] % 8 == 0 and lay["flag_off"] % 4 == 0, (name, world, lay)
             assert lay["n"] == lay["flag_off"] + P2P_FLAG_WORDS
+
+
+def test_actor_critic_configs_equal_the_reference_files():
+    """config.{ddpg,td3,sac}.*  are generated from tables; where the reference is present they must equal its
+    shipped config modules key for key (including td3/cartpole.py's two keys the constructor silently ignores)."""
+    from jorldy_b200 import config as cfg
+    paths = [p for p in cfg.available() if p.split(".")[1] in ("ddpg", "td3", "sac")]
+    assert len(paths) == 8
+    for p in paths:
+        mine = cfg.load(p)
+        assert mine.agent["name"] == p.split(".")[1] and mine.optim["actor"] == "adam"
+        ref_file = os.path.join("/root/reference/jorldy", *p.split(".")) + ".py"
+        if os.path.exists(ref_file):
+            ref = {}
+            exec(open(ref_file).read(), ref)
+            for sec in ("env", "agent", "optim", "train"):
+                assert getattr(mine, sec) == ref[sec], (p, sec)
