@@ -911,7 +911,8 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_sec / args.steps, "higher_is_better": True,
             "scaling": wl.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": wl.config(), "reference_sample": wl.reference_sample(), "reference_actors": 8 if args.config.startswith("ppo") else 1,
+            "config": make_workload(args.config, args, max(1, args.gpus)).config(),      # the GPU arm's config at this N
+            "reference_sample": wl.reference_sample(), "reference_actors": 8 if args.config.startswith("ppo") else 1,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_cores(), "threads": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
