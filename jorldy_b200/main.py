@@ -10,10 +10,13 @@ default_config_path = "config.dqn.cartpole"
 
 def main(argv=None):
     parser = argparse.ArgumentParser()
-    parser.add_argument("--single", action="store_true")
-    parser.add_argument("--sync", action="store_true")
-    parser.add_argument("--async", action="store_true")
-    parser.add_argument("--eval", action="store_true")
+    parser.add_argument("--single", action="store_true", help="the reference's per-step loop, one env (default)")
+    parser.add_argument("--sync", action="store_true",
+                        help="GPU-resident pipeline: train.num_workers batched envs + learner on one device (one rank per GPU under torchrun)")
+    parser.add_argument("--async", action="store_true",
+                        help="same pipeline as --sync: collection and learning share the device, there is no separate interact process "
+                             "to be asynchronous with")
+    parser.add_argument("--eval", action="store_true", help="greedy episodes from train.load_path")
     parser.add_argument("--config", type=str, help="config.dqn.cartpole")
     args, unknown = parser.parse_known_args(argv)
     n_modes = args.single + args.sync + args.__dict__["async"] + args.eval
