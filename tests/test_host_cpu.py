@@ -175,3 +175,24 @@ def test_actor_critic_configs_equal_the_reference_files():
             exec(open(ref_file).read(), ref)
             for sec in ("env", "agent", "optim", "train"):
                 assert getattr(mine, sec) == ref[sec], (p, sec)
+
+
+def test_public_headers_are_plain_c99(tmp_path):
+    """The drop-in boundary is a C ABI: both public headers must compile as C99 (-pedantic -Werror) — no C++ types, no torch
+    types, plain pointers and sizes — and the fused-args struct must have the size its ctypes mirror assumes."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include <stdio.h>\n#include "jorldy_b200.h"\n#include "jorldy_b200_fused.h"\n'
+                   'int main(void) { printf("%zu\\n", sizeof(jb_ppo_fused_args)); return 0; }\n')
+    exe = tmp_path / "hdr"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    size = int(subprocess.run([str(exe)], capture_output=True, text=True).stdout)
+    import ctypes
+    from jorldy_b200.core.agent.ppo_fused import FusedArgs
+    assert size == ctypes.sizeof(FusedArgs)
